@@ -1,0 +1,290 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+ctypes/numpy wrapper over oracle/liboracle.so (the CPU restatement of the reference hot path,
+oracle/bls12_381_oracle.hpp).  Importable only from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package bls12_381_b200 never imports this.
+
+Array conventions (identical to include/bls12381_b200.h): uint64 little-endian limbs, Montgomery form;
+Fp (n,6)  Fp2 (n,12)  Fp6 (n,36)  Fp12 (n,72)  G1 affine (n,12)+inf(n,) uint8  G1 projective (n,18)
+G2 affine (n,24)+inf  G2 projective (n,36)  scalars (n,32) uint8 canonical little-endian.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_DIR, "liboracle.so")
+
+
+def build(force=False):
+    src = [os.path.join(_DIR, f) for f in ("oracle_capi.cpp", "bls12_381_oracle.hpp")]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
+        subprocess.check_call(["make", "-C", _DIR, "-s", "liboracle.so"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = C.CDLL(_SO)
+        _lib.orc_tower_op.restype = C.c_int
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _u64(a, width):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    return a.reshape(-1, width)
+
+
+def _u8(a, width=None):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a if width is None else a.reshape(-1, width)
+
+
+def hardware_threads():
+    return int(lib().orc_hardware_threads())
+
+
+OPS = dict(mul=0, add=1, sub=2, square=3, neg=4, invert=5, frobenius=6, conjugate=7, mul_by_nonresidue=8,
+           cyclotomic_square=9)
+WIDTH = {1: 6, 2: 12, 6: 36, 12: 72}
+
+
+def tower(level, op, a, b=None):
+    w = WIDTH[level]
+    a = _u64(a, w)
+    if b is not None:
+        b = _u64(b, w)
+    out = np.empty_like(a)
+    rc = lib().orc_tower_op(level, OPS[op], _p(a), _p(b), _p(out), C.c_size_t(a.shape[0]))
+    if rc != 0:
+        raise ValueError("oracle: unsupported op %s at level %d" % (op, level))
+    return out
+
+
+def fp12_mul_by_014(f, c0, c1, c4):
+    f = _u64(f, 72)
+    c0, c1, c4 = _u64(c0, 12), _u64(c1, 12), _u64(c4, 12)
+    out = np.empty_like(f)
+    lib().orc_fp12_mul_by_014(_p(f), _p(c0), _p(c1), _p(c4), _p(out), C.c_size_t(f.shape[0]))
+    return out
+
+
+def fp_sqrt(a):
+    a = _u64(a, 6)
+    out = np.empty_like(a)
+    ok = lib().orc_fp_sqrt(_p(a), _p(out))
+    return bool(ok), out
+
+
+def fp2_sqrt(a):
+    a = _u64(a, 12)
+    out = np.empty_like(a)
+    ok = lib().orc_fp2_sqrt(_p(a), _p(out))
+    return bool(ok), out
+
+
+def fp_from_bytes(b):
+    b = _u8(b)
+    out = np.empty((1, 6), np.uint64)
+    ok = lib().orc_fp_from_bytes(_p(b), _p(out))
+    return bool(ok), out
+
+
+def fp_to_bytes(a):
+    a = _u64(a, 6)
+    out = np.empty(48, np.uint8)
+    lib().orc_fp_to_bytes(_p(a), _p(out))
+    return out
+
+
+def fp_lex_largest(a):
+    return bool(lib().orc_fp_lex_largest(_p(_u64(a, 6))))
+
+
+def scalar_from_wide(wide):
+    wide = _u8(wide, 64)
+    out = np.empty((wide.shape[0], 32), np.uint8)
+    lib().orc_scalar_from_wide(_p(wide), _p(out), C.c_size_t(wide.shape[0]))
+    return out
+
+
+def scalar_to_bytes(mont):
+    mont = _u64(mont, 4)
+    out = np.empty((mont.shape[0], 32), np.uint8)
+    lib().orc_scalar_to_bytes(_p(mont), _p(out), C.c_size_t(mont.shape[0]))
+    return out
+
+
+class _Group:
+    """G1 (k=1) or G2 (k=2) entry points; coordinates are k*6 limbs wide."""
+
+    def __init__(self, k):
+        self.k = k
+        self.aw = 12 * k
+        self.pw = 18 * k
+        self.n = "g%d" % k
+
+    def _f(self, name):
+        return getattr(lib(), "orc_%s_%s" % (self.n, name))
+
+    def generator(self):
+        out = np.empty((1, self.pw), np.uint64)
+        self._f("generator")(_p(out))
+        return out
+
+    def identity(self, n=1):
+        out = np.zeros((n, self.pw), np.uint64)
+        out[:, 6 * self.k:6 * self.k + 6] = R_LIMBS
+        return out
+
+    def affine_identity(self, n=1):
+        out = np.zeros((n, self.aw), np.uint64)
+        out[:, 6 * self.k:6 * self.k + 6] = R_LIMBS
+        return out, np.ones(n, np.uint8)
+
+    def double(self, p):
+        p = _u64(p, self.pw)
+        out = np.empty_like(p)
+        self._f("double")(_p(p), _p(out), C.c_size_t(p.shape[0]))
+        return out
+
+    def add(self, p, q):
+        p, q = _u64(p, self.pw), _u64(q, self.pw)
+        out = np.empty_like(p)
+        self._f("add")(_p(p), _p(q), _p(out), C.c_size_t(p.shape[0]))
+        return out
+
+    def add_mixed(self, p, qxy, qinf=None):
+        p, qxy = _u64(p, self.pw), _u64(qxy, self.aw)
+        qinf = None if qinf is None else _u8(qinf)
+        out = np.empty_like(p)
+        self._f("add_mixed")(_p(p), _p(qxy), _p(qinf), _p(out), C.c_size_t(p.shape[0]))
+        return out
+
+    def mul(self, p, s, threads=1):
+        p, s = _u64(p, self.pw), _u8(s, 32)
+        out = np.empty_like(p)
+        self._f("mul")(_p(p), _p(s), _p(out), C.c_size_t(p.shape[0]), threads)
+        return out
+
+    def to_affine(self, p):
+        p = _u64(p, self.pw)
+        xy = np.empty((p.shape[0], self.aw), np.uint64)
+        inf = np.empty(p.shape[0], np.uint8)
+        self._f("to_affine")(_p(p), _p(xy), _p(inf), C.c_size_t(p.shape[0]))
+        return xy, inf
+
+    def batch_normalize(self, p):
+        p = _u64(p, self.pw)
+        xy = np.empty((p.shape[0], self.aw), np.uint64)
+        inf = np.empty(p.shape[0], np.uint8)
+        self._f("batch_normalize")(_p(p), _p(xy), _p(inf), C.c_size_t(p.shape[0]))
+        return xy, inf
+
+    def from_affine(self, xy, inf=None):
+        xy = _u64(xy, self.aw)
+        n = xy.shape[0]
+        out = np.zeros((n, self.pw), np.uint64)
+        out[:, :self.aw] = xy
+        z = np.zeros((n, 6 * self.k), np.uint64)
+        z[:, :6] = R_LIMBS
+        if inf is not None:
+            z[np.asarray(inf) != 0] = 0
+        out[:, self.aw:] = z
+        return out
+
+    def msm_naive(self, xy, inf, s, threads=1):
+        xy, s = _u64(xy, self.aw), _u8(s, 32)
+        inf = None if inf is None else _u8(inf)
+        out = np.empty((1, self.pw), np.uint64)
+        self._f("msm_naive")(_p(xy), _p(inf), _p(s), C.c_size_t(xy.shape[0]), _p(out), threads)
+        return out
+
+    def msm_pippenger(self, xy, inf, s, c=8, threads=1):
+        xy, s = _u64(xy, self.aw), _u8(s, 32)
+        inf = None if inf is None else _u8(inf)
+        out = np.empty((1, self.pw), np.uint64)
+        self._f("msm_pippenger")(_p(xy), _p(inf), _p(s), C.c_size_t(xy.shape[0]), _p(out), c, threads)
+        return out
+
+    def to_compressed(self, xy, inf=0):
+        out = np.empty(48 * self.k, np.uint8)
+        self._f("to_compressed")(_p(_u64(xy, self.aw)), int(inf), _p(out))
+        return out
+
+    def to_uncompressed(self, xy, inf=0):
+        out = np.empty(96 * self.k, np.uint8)
+        self._f("to_uncompressed")(_p(_u64(xy, self.aw)), int(inf), _p(out))
+        return out
+
+    def from_compressed(self, b):
+        xy = np.empty((1, self.aw), np.uint64)
+        inf = np.zeros(1, np.uint8)
+        ok = self._f("from_compressed")(_p(_u8(b)), _p(xy), _p(inf))
+        return bool(ok), xy, int(inf[0])
+
+    def from_uncompressed(self, b):
+        xy = np.empty((1, self.aw), np.uint64)
+        inf = np.zeros(1, np.uint8)
+        ok = self._f("from_uncompressed")(_p(_u8(b)), _p(xy), _p(inf))
+        return bool(ok), xy, int(inf[0])
+
+
+R_LIMBS = np.array([0x760900000002fffd, 0xebf4000bc40c0002, 0x5f48985753c758ba, 0x77ce585370525745,
+                    0x5c071a97a256ec6d, 0x15f65ec3fa80e493], dtype=np.uint64)
+G1 = _Group(1)
+G2 = _Group(2)
+
+
+def _pairs(pxy, pinf, qxy, qinf):
+    pxy, qxy = _u64(pxy, 12), _u64(qxy, 24)
+    pinf = None if pinf is None else _u8(pinf)
+    qinf = None if qinf is None else _u8(qinf)
+    return pxy, pinf, qxy, qinf
+
+
+def miller_loop(pxy, pinf, qxy, qinf, threads=1):
+    pxy, pinf, qxy, qinf = _pairs(pxy, pinf, qxy, qinf)
+    out = np.empty((pxy.shape[0], 72), np.uint64)
+    lib().orc_miller_loop(_p(pxy), _p(pinf), _p(qxy), _p(qinf), C.c_size_t(pxy.shape[0]), _p(out), threads)
+    return out
+
+
+def final_exponentiation(f, threads=1):
+    f = _u64(f, 72)
+    out = np.empty_like(f)
+    lib().orc_final_exp(_p(f), C.c_size_t(f.shape[0]), _p(out), threads)
+    return out
+
+
+def pairing(pxy, pinf, qxy, qinf, threads=1):
+    pxy, pinf, qxy, qinf = _pairs(pxy, pinf, qxy, qinf)
+    out = np.empty((pxy.shape[0], 72), np.uint64)
+    lib().orc_pairing(_p(pxy), _p(pinf), _p(qxy), _p(qinf), C.c_size_t(pxy.shape[0]), _p(out), threads)
+    return out
+
+
+def multi_miller_loop(pxy, pinf, qxy, qinf):
+    pxy, pinf, qxy, qinf = _pairs(pxy, pinf, qxy, qinf)
+    out = np.empty((1, 72), np.uint64)
+    lib().orc_multi_miller_loop(_p(pxy), _p(pinf), _p(qxy), _p(qinf), C.c_size_t(pxy.shape[0]), _p(out))
+    return out
+
+
+def g2_prepare(qxy, qinf=0):
+    out = np.empty((68, 36), np.uint64)
+    n = lib().orc_g2_prepare(_p(_u64(qxy, 24)), int(qinf), _p(out))
+    assert n == 68
+    return out
