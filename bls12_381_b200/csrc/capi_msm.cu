@@ -1,0 +1,350 @@
+// C ABI, part 3: Pippenger bucket multi-scalar multiplication for G1 and G2 (BASELINE configs 2, 3, 5).
+//
+// The reference has no MSM: it can only express sum_i p_i * s_i as N constant-time 255-step
+// double-and-adds folded with `+` (src/g1.rs:573-579, :754-774, :161-171).  This file
+// computes the same group element with the bucket method, reorganised for a B200:
+//
+//   1. k_msm_count    signed c-bit window digits of every scalar -> per-(window,bucket) histogram
+//   2. k_msm_scan     exclusive scan of the histogram (one block per window)
+//   3. k_msm_scatter  counting-sort scatter: point index (+ sign bit) grouped by bucket
+//   4. k_msm_accumulate  one thread per bucket: complete mixed additions of its points (the 126 MB L2
+//                     holds the whole 96/192 MB point set, so the gathers are L2 hits)
+//   5. k_msm_reduce   sum_b (b+1) * B_b per window: per-thread running sums over a chunk of buckets,
+//                     chunk offset by a short double-and-add, shared-memory tree per block
+//   6. k_msm_combine  sums the per-block partials and runs Horner over the windows
+//
+// All additions are the reference's COMPLETE formulas (curve.cuh), so duplicate points, P + (-P),
+// identity inputs and zero scalars need no special cases.  Window sharding (shard, n_shards) restricts
+// steps 1-5 to windows w = shard (mod n_shards); step 6 then yields sum_{w in shard} 2^(cw) S_w.
+#include "ctx.cuh"
+#include "curve.cuh"
+
+using namespace b200;
+
+namespace {
+
+constexpr int MAX_WINDOWS = 128;
+
+struct msm_plan {
+  int c;          // window bits
+  int nwin;       // total windows = ceil(256 / c)
+  int nloc;       // windows handled by this shard
+  int nbuckets;   // 2^(c-1) per window
+  int win[MAX_WINDOWS];  // global index of local window j
+};
+
+// signed digit of window w for a canonical 256-bit little-endian scalar held in 8 words.
+// digits d_w in [-2^(c-1), 2^(c-1)], sum_w d_w 2^(cw) == s.  Returns magnitude and sign.
+__device__ __forceinline__ uint32_t window_bits(const uint32_t s[8], int lo, int c) {
+  // bits [lo, lo+c) of s, zero beyond bit 255
+  int word = lo >> 5, sh = lo & 31;
+  uint64_t v = 0;
+  if (word < 8) v = s[word];
+  if (word + 1 < 8) v |= (uint64_t)s[word + 1] << 32;
+  return (uint32_t)(v >> sh) & ((1u << c) - 1u);
+}
+
+__device__ __forceinline__ void load_scalar(uint32_t s[8], const uint32_t *scalars, size_t i) {
+  const uint4 *sp = reinterpret_cast<const uint4 *>(scalars + 8 * i);
+  uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
+  s[0] = lo.x; s[1] = lo.y; s[2] = lo.z; s[3] = lo.w;
+  s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
+}
+
+// Walks the windows of scalar i; calls f(local_window_index, bucket (0-based magnitude-1), negative)
+// for every non-zero digit whose window belongs to this shard.
+template <class Fn>
+__device__ __forceinline__ void for_each_digit(const msm_plan &pl, const uint32_t s[8], Fn f) {
+  uint32_t carry = 0;
+  int j = 0;
+  const uint32_t half = 1u << (pl.c - 1);
+  for (int w = 0; w < pl.nwin; w++) {
+    uint32_t d = window_bits(s, w * pl.c, pl.c) + carry;
+    bool neg = d > half;
+    carry = neg ? 1u : 0u;
+    uint32_t mag = neg ? (1u << pl.c) - d : d;
+    if (j < pl.nloc && pl.win[j] == w) {
+      if (mag != 0) f(j, mag - 1u, neg);
+      j++;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_msm_count(msm_plan pl, const uint32_t *scalars, const uint8_t *inf, size_t n,
+                                                 uint32_t *hist) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (inf && inf[i]) return;
+  uint32_t s[8];
+  load_scalar(s, scalars, i);
+  for_each_digit(pl, s, [&](int j, uint32_t b, bool) { atomicAdd(&hist[(size_t)j * pl.nbuckets + b], 1u); });
+}
+
+// one block per local window: offsets[b] = exclusive prefix of hist over buckets; cursor := 0
+__global__ void __launch_bounds__(1024) k_msm_scan(int nbuckets, const uint32_t *hist, uint32_t *offsets) {
+  __shared__ uint32_t part[1024];
+  const uint32_t *h = hist + (size_t)blockIdx.x * nbuckets;
+  uint32_t *o = offsets + (size_t)blockIdx.x * nbuckets;
+  int per = (nbuckets + blockDim.x - 1) / blockDim.x;
+  int lo = threadIdx.x * per, hi = min(lo + per, nbuckets);
+  uint32_t sum = 0;
+  for (int b = lo; b < hi; b++) sum += h[b];
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  // Hillis–Steele inclusive scan over the 1024 partials
+  for (int off = 1; off < (int)blockDim.x; off <<= 1) {
+    uint32_t v = threadIdx.x >= (unsigned)off ? part[threadIdx.x - off] : 0;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  uint32_t run = part[threadIdx.x] - sum;
+  for (int b = lo; b < hi; b++) {
+    uint32_t c = h[b];
+    o[b] = run;
+    run += c;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_msm_scatter(msm_plan pl, const uint32_t *scalars, const uint8_t *inf, size_t n,
+                                                   const uint32_t *offsets, uint32_t *cursor, uint32_t *sorted) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (inf && inf[i]) return;
+  uint32_t s[8];
+  load_scalar(s, scalars, i);
+  for_each_digit(pl, s, [&](int j, uint32_t b, bool neg) {
+    size_t k = (size_t)j * pl.nbuckets + b;
+    uint32_t pos = offsets[k] + atomicAdd(&cursor[k], 1u);
+    sorted[(size_t)j * n + pos] = (uint32_t)i | (neg ? 0x80000000u : 0u);
+  });
+}
+
+// one thread per (local window, bucket)
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_accumulate(int nbuckets, size_t total, const char *points, size_t n,
+                                                      const uint32_t *offsets, const uint32_t *hist,
+                                                      const uint32_t *sorted, char *buckets) {
+  size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (k >= total) return;
+  constexpr size_t FB = field_traits<F>::bytes, AB = 2 * FB, PB = 3 * FB;
+  size_t j = k / nbuckets;
+  const uint32_t *idx = sorted + j * n + offsets[k];
+  uint32_t cnt = hist[k];
+  proj<F> acc = proj_identity<F>();
+  for (uint32_t t = 0; t < cnt; t++) {
+    uint32_t e = __ldg(idx + t);
+    const char *pp = points + AB * (size_t)(e & 0x7fffffffu);
+    F x = field_traits<F>::load_ro(pp), y = field_traits<F>::load_ro(pp + FB);
+    if (e >> 31) y = f_neg(y);
+    acc = proj_add_mixed_nz(acc, x, y);
+  }
+  proj_store<F>(buckets + PB * k, acc);
+}
+
+// small multiple k * P, k < 2^24, by double-and-add (MSB first)
+template <class F>
+__device__ proj<F> proj_mul_small(const proj<F> &p, uint32_t k) {
+  proj<F> acc = proj_identity<F>();
+  if (k == 0) return acc;
+  int top = 31 - __clz(k);
+#pragma unroll 1
+  for (int b = top; b >= 0; b--) {
+    acc = proj_double(acc);
+    if ((k >> b) & 1) acc = proj_add(acc, p);
+  }
+  return acc;
+}
+
+// grid = (blocks_per_window, nloc).  Thread handles `chunk` consecutive buckets.
+template <class F, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_msm_reduce(int nbuckets, int chunk, const char *buckets, char *partials) {
+  extern __shared__ char smem[];
+  constexpr size_t PB = 3 * field_traits<F>::bytes;
+  int j = blockIdx.y;
+  int t = blockIdx.x * BLOCK + threadIdx.x;       // chunk index within the window
+  int lo = t * chunk, hi = min(lo + chunk, nbuckets);
+  const char *wb = buckets + PB * (size_t)j * nbuckets;
+  proj<F> run = proj_identity<F>(), acc = proj_identity<F>();
+  for (int b = hi - 1; b >= lo; b--) {
+    run = proj_add(run, proj_load<F>(wb + PB * b));
+    acc = proj_add(acc, run);
+  }
+  // acc = sum (b - lo + 1) B_b ; bucket b is worth (b + 1):  add lo * run
+  if (lo > 0 && lo < nbuckets) acc = proj_add(acc, proj_mul_small(run, (uint32_t)lo));
+  proj_store<F>(smem + PB * threadIdx.x, acc);
+  __syncthreads();
+  for (int s = BLOCK / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+      proj<F> a = proj_load<F>(smem + PB * threadIdx.x), b2 = proj_load<F>(smem + PB * (threadIdx.x + s));
+      proj_store<F>(smem + PB * threadIdx.x, proj_add(a, b2));
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) proj_store<F>(partials + PB * ((size_t)j * gridDim.x + blockIdx.x), proj_load<F>(smem));
+}
+
+// one block: thread j (< nloc) sums the partials of local window j; thread 0 then runs Horner over
+// ALL windows (identity for windows of other shards): out = sum_{w in shard} 2^(c w) S_w
+template <class F>
+__global__ void __launch_bounds__(MAX_WINDOWS) k_msm_combine(msm_plan pl, int parts_per_window, const char *partials,
+                                                           char *out) {
+  extern __shared__ char smem[];
+  constexpr size_t PB = 3 * field_traits<F>::bytes;
+  int j = threadIdx.x;
+  if (j < pl.nloc) {
+    proj<F> acc = proj_identity<F>();
+    for (int k = 0; k < parts_per_window; k++) acc = proj_add(acc, proj_load<F>(partials + PB * ((size_t)j * parts_per_window + k)));
+    proj_store<F>(smem + PB * j, acc);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    proj<F> acc = proj_identity<F>();
+    int jj = pl.nloc - 1;
+#pragma unroll 1
+    for (int w = pl.nwin - 1; w >= 0; w--) {
+      if (jj >= 0 && pl.win[jj] == w) {
+        acc = proj_add(acc, proj_load<F>(smem + PB * jj));
+        jj--;
+      }
+      if (w > 0) {
+#pragma unroll 1
+        for (int k = 0; k < pl.c; k++) acc = proj_double(acc);
+      }
+    }
+    proj_store<F>(out, acc);
+  }
+}
+
+template <class F>
+__global__ void k_store_identity(char *out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) proj_store<F>(out, proj_identity<F>());
+}
+
+inline unsigned nblk(size_t n, unsigned b) { return (unsigned)((n + b - 1) / b); }
+
+int auto_window(size_t n) {
+  // minimise  W * n (bucket adds) + W * 2^(c-1) * ~3 (reduction) ; measured sweet spots on B200
+  int lg = 0;
+  while (((size_t)1 << (lg + 1)) <= n) lg++;
+  int c = lg - 4;
+  if (c < 4) c = 4;
+  if (c > 16) c = 16;
+  return c;
+}
+
+template <class F>
+int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scalars, size_t n, int shard, int n_shards,
+            void *out) {
+  constexpr size_t PB = 3 * field_traits<F>::bytes;
+  if (n_shards < 1 || shard < 0 || shard >= n_shards) return B200_EINVAL;
+  if (n >= ((size_t)1 << 31)) return B200_EINVAL;
+  msm_plan pl;
+  pl.c = ctx->msm_c ? ctx->msm_c : auto_window(n);
+  pl.nwin = (256 + pl.c - 1) / pl.c;
+  if (pl.nwin > MAX_WINDOWS) return B200_EINVAL;
+  pl.nbuckets = 1 << (pl.c - 1);
+  pl.nloc = 0;
+  for (int w = shard; w < pl.nwin; w += n_shards) pl.win[pl.nloc++] = w;
+  if (n == 0 || pl.nloc == 0) {
+    B200_LAUNCH(ctx, k_store_identity<F>, 1, 32, 0, (char *)out);
+    return B200_OK;
+  }
+  size_t total = (size_t)pl.nloc * pl.nbuckets;
+  // reduction geometry
+  constexpr int RB = sizeof(F) == sizeof(fp) ? 128 : 64;  // block size (smem: RB * PB)
+  int chunks = pl.nbuckets >= 2048 ? 2048 : pl.nbuckets;  // threads per window (power of two)
+  if (chunks < RB) chunks = RB;
+  int chunk = (pl.nbuckets + chunks - 1) / chunks;
+  if (chunk < 1) chunk = 1;
+  int blocks_per_window = chunks / RB;
+  size_t need = 3 * arena_pad(total * 4) + arena_pad((size_t)pl.nloc * n * 4) + arena_pad(total * PB) +
+                arena_pad((size_t)pl.nloc * blocks_per_window * PB) + 4096;
+  int rc = arena_reserve(ctx, need);
+  if (rc != B200_OK) return rc;
+  uint32_t *hist = arena_take<uint32_t>(ctx, total);
+  uint32_t *cursor = arena_take<uint32_t>(ctx, total);
+  uint32_t *offsets = arena_take<uint32_t>(ctx, total);
+  uint32_t *sorted = arena_take<uint32_t>(ctx, (size_t)pl.nloc * n);
+  char *buckets = arena_take<char>(ctx, total * PB);
+  char *partials = arena_take<char>(ctx, (size_t)pl.nloc * blocks_per_window * PB);
+  // hist and cursor are adjacent: one memset
+  B200_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)((char *)offsets - (char *)hist), ctx->stream));
+  B200_LAUNCH(ctx, k_msm_count, nblk(n, 256), 256, 0, pl, (const uint32_t *)scalars, (const uint8_t *)inf, n, hist);
+  B200_LAUNCH(ctx, k_msm_scan, pl.nloc, 1024, 0, pl.nbuckets, hist, offsets);
+  B200_LAUNCH(ctx, k_msm_scatter, nblk(n, 256), 256, 0, pl, (const uint32_t *)scalars, (const uint8_t *)inf, n, offsets,
+              cursor, sorted);
+  B200_LAUNCH(ctx, k_msm_accumulate<F>, nblk(total, 128), 128, 0, pl.nbuckets, total, (const char *)points, n, offsets,
+              hist, sorted, buckets);
+  dim3 rgrid(blocks_per_window, pl.nloc);
+  B200_LAUNCH(ctx, (k_msm_reduce<F, RB>), rgrid, RB, RB * PB, pl.nbuckets, chunk, buckets, partials);
+  B200_LAUNCH(ctx, k_msm_combine<F>, 1, MAX_WINDOWS, (size_t)pl.nloc * PB, pl, blocks_per_window, partials, (char *)out);
+  return B200_OK;
+}
+
+template <class F>
+int msm_host(b200_ctx *ctx, const void *points, const uint8_t *inf, const void *scalars, size_t n, void *out) {
+  constexpr size_t FB = field_traits<F>::bytes, AB = 2 * FB, PB = 3 * FB;
+  int rc = stage_reserve(ctx, AB * n + 32 * n + n + PB + 8 * 256);
+  if (rc != B200_OK) return rc;
+  void *dp = stage_take(ctx, AB * n), *ds = stage_take(ctx, 32 * n), *di = inf ? stage_take(ctx, n) : nullptr;
+  void *dout = stage_take(ctx, PB);
+  if (n) {
+    B200_CUDA(ctx, cudaMemcpyAsync(dp, points, AB * n, cudaMemcpyHostToDevice, ctx->stream));
+    B200_CUDA(ctx, cudaMemcpyAsync(ds, scalars, 32 * n, cudaMemcpyHostToDevice, ctx->stream));
+    if (inf) B200_CUDA(ctx, cudaMemcpyAsync(di, inf, n, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  rc = msm_dev<F>(ctx, dp, di, ds, n, 0, 1, dout);
+  if (rc != B200_OK) return rc;
+  B200_CUDA(ctx, cudaMemcpyAsync(out, dout, PB, cudaMemcpyDeviceToHost, ctx->stream));
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+}  // namespace
+
+#define CHECK_CTX(ctx)                      \
+  if ((ctx) == nullptr) return B200_EINVAL; \
+  ctx_guard guard__(ctx);                   \
+  if (!guard__.ok) return B200_ENODEV
+
+extern "C" {
+
+int b200_g1_msm_shard_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scalars, size_t n, int shard,
+                          int n_shards, void *out) {
+  CHECK_CTX(ctx);
+  if (!out || (n && (!points || !scalars))) return B200_EINVAL;
+  int rc = msm_dev<fp>(ctx, points, inf, scalars, n, shard, n_shards, out);
+  if (rc != B200_OK) return rc;
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+int b200_g2_msm_shard_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scalars, size_t n, int shard,
+                          int n_shards, void *out) {
+  CHECK_CTX(ctx);
+  if (!out || (n && (!points || !scalars))) return B200_EINVAL;
+  int rc = msm_dev<fp2>(ctx, points, inf, scalars, n, shard, n_shards, out);
+  if (rc != B200_OK) return rc;
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+int b200_g1_msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scalars, size_t n, void *out) {
+  return b200_g1_msm_shard_dev(ctx, points, inf, scalars, n, 0, 1, out);
+}
+int b200_g2_msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scalars, size_t n, void *out) {
+  return b200_g2_msm_shard_dev(ctx, points, inf, scalars, n, 0, 1, out);
+}
+int b200_g1_msm(b200_ctx *ctx, const b200_g1_affine *points, const uint8_t *inf, const b200_scalar *scalars, size_t n,
+                b200_g1_projective *out) {
+  CHECK_CTX(ctx);
+  if (!out || (n && (!points || !scalars))) return B200_EINVAL;
+  return msm_host<fp>(ctx, points, inf, scalars, n, out);
+}
+int b200_g2_msm(b200_ctx *ctx, const b200_g2_affine *points, const uint8_t *inf, const b200_scalar *scalars, size_t n,
+                b200_g2_projective *out) {
+  CHECK_CTX(ctx);
+  if (!out || (n && (!points || !scalars))) return B200_EINVAL;
+  return msm_host<fp2>(ctx, points, inf, scalars, n, out);
+}
+
+}  // extern "C"

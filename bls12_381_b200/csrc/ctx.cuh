@@ -1,0 +1,102 @@
+// b200_ctx: one CUDA device, one stream, grow-only scratch arena, launch counter, last-error text.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/bls12381_b200.h"
+
+struct b200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+  char err[256] = {0};
+  uint64_t launches = 0;
+  int msm_c = 0;
+  int sm_count = 148;
+  // scratch arena (device memory), bump-allocated per API call
+  char *arena = nullptr;
+  size_t arena_size = 0, arena_off = 0;
+  // staging arena for the host-pointer entry points
+  char *stage = nullptr;
+  size_t stage_size = 0, stage_off = 0;
+};
+
+namespace b200 {
+
+inline int set_err(b200_ctx *ctx, cudaError_t e, const char *what) {
+  snprintf(ctx->err, sizeof(ctx->err), "%s: %s", what, cudaGetErrorString(e));
+  return e == cudaErrorMemoryAllocation ? B200_ENOMEM : B200_ECUDA;
+}
+#define B200_CUDA(ctx, call)                                         \
+  do {                                                               \
+    cudaError_t e__ = (call);                                        \
+    if (e__ != cudaSuccess) return b200::set_err(ctx, e__, #call);   \
+  } while (0)
+
+// make sure the scratch arena holds `bytes` and reset the bump pointer
+inline int arena_reserve(b200_ctx *ctx, size_t bytes) {
+  ctx->arena_off = 0;
+  if (bytes <= ctx->arena_size) return B200_OK;
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->arena) cudaFree(ctx->arena);
+  ctx->arena = nullptr;
+  ctx->arena_size = 0;
+  size_t want = bytes + (bytes >> 3) + (1 << 20);
+  B200_CUDA(ctx, cudaMalloc((void **)&ctx->arena, want));
+  ctx->arena_size = want;
+  return B200_OK;
+}
+template <class T>
+inline T *arena_take(b200_ctx *ctx, size_t count) {
+  size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+  T *p = reinterpret_cast<T *>(ctx->arena + ctx->arena_off);
+  ctx->arena_off += bytes;
+  return p;  // caller guarantees arena_reserve covered the total
+}
+inline size_t arena_pad(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+
+inline int stage_reserve(b200_ctx *ctx, size_t bytes) {
+  ctx->stage_off = 0;
+  if (bytes <= ctx->stage_size) return B200_OK;
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->stage) cudaFree(ctx->stage);
+  ctx->stage = nullptr;
+  ctx->stage_size = 0;
+  size_t want = bytes + (1 << 16);
+  B200_CUDA(ctx, cudaMalloc((void **)&ctx->stage, want));
+  ctx->stage_size = want;
+  return B200_OK;
+}
+inline void *stage_take(b200_ctx *ctx, size_t bytes) {
+  void *p = ctx->stage + ctx->stage_off;
+  ctx->stage_off += (bytes + 255) & ~(size_t)255;
+  return p;
+}
+
+#define B200_LAUNCH(ctx, kernel, grid, block, smem, ...)                                 \
+  do {                                                                                   \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                     \
+    (ctx)->launches++;                                                                   \
+    cudaError_t e__ = cudaGetLastError();                                                \
+    if (e__ != cudaSuccess) return b200::set_err(ctx, e__, "launch " #kernel);           \
+  } while (0)
+
+struct ctx_guard {
+  b200_ctx *c;
+  int prev = -1;
+  bool ok = true;
+  explicit ctx_guard(b200_ctx *ctx) : c(ctx) {
+    c->mu.lock();
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != c->device && cudaSetDevice(c->device) != cudaSuccess) ok = false;
+  }
+  ~ctx_guard() {
+    if (prev >= 0 && prev != c->device) cudaSetDevice(prev);
+    c->mu.unlock();
+  }
+};
+
+}  // namespace b200

@@ -1,0 +1,274 @@
+// Fp = GF(p), p the 381-bit BLS12-381 base-field modulus.  Device-side arithmetic for sm_100a.
+//
+// Replaces src/fp.rs of the reference (Fp type :15, add :382, neg :396, sub :421, mul :565, square :613,
+// montgomery_reduce :487, invert :346).  Same VALUE semantics: 6x64-bit little-endian limbs in memory,
+// Montgomery form with R = 2^384, every stored result canonical (< p), so results are bit-identical
+// to the reference (the canonical representative is unique).
+//
+// NOT the same algorithm: the reference does a 6x6 64-bit schoolbook product followed by a separate
+// HAC-14.32 reduction.  A B200 SM has no 64-bit multiplier: the integer datapath is the 32x32+64->64
+// IMAD.WIDE.U32 on the FMA pipe.  So an element lives in 12 x 32-bit registers and mul is a word-serial
+// interleaved (CIOS-style) Montgomery product in which the partial products are split into an
+// "even-aligned" and an "odd-aligned" accumulator so every row is ONE carry chain of
+// mad.lo.cc/madc.hi.cc pairs that ptxas fuses into IMAD.WIDE.U32(.X) — 12 wide-IMADs per row for
+// a*b_i, 12 for m*p, 1 for m: 300 IMADs per multiplication, no carry ripple between lo/hi halves.
+#pragma once
+#include <cstdint>
+
+namespace b200 {
+
+#define B200_DEV __device__ __forceinline__
+
+struct fp {
+  uint32_t v[12];
+};
+
+// p, little-endian 32-bit words  (src/fp.rs:70-77)
+#define FP_P0 0xffffaaabu
+#define FP_P1 0xb9feffffu
+#define FP_P2 0xb153ffffu
+#define FP_P3 0x1eabfffeu
+#define FP_P4 0xf6b0f624u
+#define FP_P5 0x6730d2a0u
+#define FP_P6 0xf38512bfu
+#define FP_P7 0x64774b84u
+#define FP_P8 0x434bacd7u
+#define FP_P9 0x4b1ba7b6u
+#define FP_P10 0x397fe69au
+#define FP_P11 0x1a0111eau
+// -p^{-1} mod 2^32 (low word of src/fp.rs:80)
+#define FP_INV32 0xfffcfffdu
+
+__device__ __constant__ const uint32_t FP_MOD[12] = {FP_P0, FP_P1, FP_P2, FP_P3, FP_P4,  FP_P5,
+                                                    FP_P6, FP_P7, FP_P8, FP_P9, FP_P10, FP_P11};
+
+B200_DEV uint32_t fp_modw(int i) {
+  switch (i) {
+    case 0: return FP_P0;
+    case 1: return FP_P1;
+    case 2: return FP_P2;
+    case 3: return FP_P3;
+    case 4: return FP_P4;
+    case 5: return FP_P5;
+    case 6: return FP_P6;
+    case 7: return FP_P7;
+    case 8: return FP_P8;
+    case 9: return FP_P9;
+    case 10: return FP_P10;
+    default: return FP_P11;
+  }
+}
+
+// R = 2^384 mod p  == Fp::one()  (src/fp.rs:83-90)
+B200_DEV fp fp_one() {
+  fp r = {{0x0002fffdu, 0x76090000u, 0xc40c0002u, 0xebf4000bu, 0x53c758bau, 0x5f489857u,
+           0x70525745u, 0x77ce5853u, 0xa256ec6du, 0x5c071a97u, 0xfa80e493u, 0x15f65ec3u}};
+  return r;
+}
+B200_DEV fp fp_zero() {
+  fp r;
+#pragma unroll
+  for (int i = 0; i < 12; i++) r.v[i] = 0;
+  return r;
+}
+
+// ---- PTX carry-chain primitives (CC.CF lives between adjacent volatile asm statements)
+B200_DEV void ptx_add_cc(uint32_t &d, uint32_t a, uint32_t b) { asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
+B200_DEV void ptx_addc_cc(uint32_t &d, uint32_t a, uint32_t b) { asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
+B200_DEV void ptx_addc(uint32_t &d, uint32_t a, uint32_t b) { asm volatile("addc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
+B200_DEV void ptx_sub_cc(uint32_t &d, uint32_t a, uint32_t b) { asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
+B200_DEV void ptx_subc_cc(uint32_t &d, uint32_t a, uint32_t b) { asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
+B200_DEV void ptx_subc(uint32_t &d, uint32_t a, uint32_t b) { asm volatile("subc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
+B200_DEV void ptx_mul_lo(uint32_t &d, uint32_t a, uint32_t b) { asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
+B200_DEV void ptx_mul_hi(uint32_t &d, uint32_t a, uint32_t b) { asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
+B200_DEV void ptx_mad_lo_cc(uint32_t &d, uint32_t a, uint32_t b, uint32_t c) { asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); }
+B200_DEV void ptx_madc_lo_cc(uint32_t &d, uint32_t a, uint32_t b, uint32_t c) { asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); }
+B200_DEV void ptx_madc_hi_cc(uint32_t &d, uint32_t a, uint32_t b, uint32_t c) { asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); }
+B200_DEV void ptx_madc_hi(uint32_t &d, uint32_t a, uint32_t b, uint32_t c) { asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); }
+
+// acc[0..12) += x[0],x[2],..,x[10] (stride-2 words of a 12-word operand starting at x) * s ; one
+// carry chain; the carry out of acc[11] is left in CC.CF for the caller.
+B200_DEV void fp_cmad_row(uint32_t *acc, const uint32_t *x, uint32_t s) {
+  ptx_mad_lo_cc(acc[0], x[0], s, acc[0]);
+  ptx_madc_hi_cc(acc[1], x[0], s, acc[1]);
+#pragma unroll
+  for (int j = 2; j < 12; j += 2) {
+    ptx_madc_lo_cc(acc[j], x[j], s, acc[j]);
+    ptx_madc_hi_cc(acc[j + 1], x[j], s, acc[j + 1]);
+  }
+}
+// same with the modulus words as immediates: which = 0 (even words p0,p2,..) or 1 (odd words p1,p3,..)
+template <int which>
+B200_DEV void fp_cmad_row_mod(uint32_t *acc, uint32_t s) {
+  ptx_mad_lo_cc(acc[0], fp_modw(which), s, acc[0]);
+  ptx_madc_hi_cc(acc[1], fp_modw(which), s, acc[1]);
+#pragma unroll
+  for (int j = 2; j < 12; j += 2) {
+    ptx_madc_lo_cc(acc[j], fp_modw(which + j), s, acc[j]);
+    ptx_madc_hi_cc(acc[j + 1], fp_modw(which + j), s, acc[j + 1]);
+  }
+}
+// acc[k] = x*s + acc[k+2] (shift right by two words while accumulating), carry-in from CC.CF
+B200_DEV void fp_madc_rshift_row(uint32_t *acc, const uint32_t *x, uint32_t s) {
+#pragma unroll
+  for (int j = 0; j < 10; j += 2) {
+    ptx_madc_lo_cc(acc[j], x[j], s, acc[j + 2]);
+    ptx_madc_hi_cc(acc[j + 1], x[j], s, acc[j + 3]);
+  }
+  ptx_madc_lo_cc(acc[10], x[10], s, 0u);
+  ptx_madc_hi(acc[11], x[10], s, 0u);
+}
+// one Montgomery reduction step on (A at word 0, B at word 1): makes A[0] == 0
+B200_DEV void fp_redc_step(uint32_t *A, uint32_t *B) {
+  uint32_t m = A[0] * FP_INV32;
+  fp_cmad_row_mod<1>(B, m);  // no carry out (value bound)
+  fp_cmad_row_mod<0>(A, m);
+  ptx_addc(B[11], B[11], 0u);
+}
+
+// r = a * b * R^-1 mod p, canonical.   (value-identical to src/fp.rs:565-609)
+B200_DEV fp fp_mul(const fp &a, const fp &b) {
+  uint32_t ev[12], od[12];
+  // row 0: plain products
+#pragma unroll
+  for (int j = 0; j < 12; j += 2) {
+    ptx_mul_lo(ev[j], a.v[j], b.v[0]);
+    ptx_mul_hi(ev[j + 1], a.v[j], b.v[0]);
+    ptx_mul_lo(od[j], a.v[j + 1], b.v[0]);
+    ptx_mul_hi(od[j + 1], a.v[j + 1], b.v[0]);
+  }
+  fp_redc_step(ev, od);
+#pragma unroll
+  for (int i = 1; i < 12; i += 2) {
+    // odd row: A = od (word aligned after the shift), B = ev (shifted in)
+    ptx_add_cc(od[0], od[0], ev[1]);
+    fp_madc_rshift_row(ev, a.v + 1, b.v[i]);
+    fp_cmad_row(od, a.v, b.v[i]);
+    ptx_addc(ev[11], ev[11], 0u);
+    fp_redc_step(od, ev);
+    if (i + 1 < 12) {
+      // even row: roles swapped back
+      ptx_add_cc(ev[0], ev[0], od[1]);
+      fp_madc_rshift_row(od, a.v + 1, b.v[i + 1]);
+      fp_cmad_row(ev, a.v, b.v[i + 1]);
+      ptx_addc(od[11], od[11], 0u);
+      fp_redc_step(ev, od);
+    }
+  }
+  // after 12 rows: "even role" = od (od[0]==0), "odd role" = ev ; result = (od >> 32) + ev  (< 2p)
+  fp r;
+  ptx_add_cc(r.v[0], ev[0], od[1]);
+#pragma unroll
+  for (int k = 1; k < 11; k++) ptx_addc_cc(r.v[k], ev[k], od[k + 1]);
+  ptx_addc(r.v[11], ev[11], 0u);
+  // conditional subtract p
+  uint32_t t[12], borrow;
+  ptx_sub_cc(t[0], r.v[0], fp_modw(0));
+#pragma unroll
+  for (int k = 1; k < 12; k++) ptx_subc_cc(t[k], r.v[k], fp_modw(k));
+  ptx_subc(borrow, 0u, 0u);
+#pragma unroll
+  for (int k = 0; k < 12; k++) r.v[k] = borrow ? r.v[k] : t[k];
+  return r;
+}
+B200_DEV fp fp_sqr(const fp &a) { return fp_mul(a, a); }
+
+// src/fp.rs:382-393
+B200_DEV fp fp_add(const fp &a, const fp &b) {
+  fp r;
+  ptx_add_cc(r.v[0], a.v[0], b.v[0]);
+#pragma unroll
+  for (int k = 1; k < 11; k++) ptx_addc_cc(r.v[k], a.v[k], b.v[k]);
+  ptx_addc(r.v[11], a.v[11], b.v[11]);
+  uint32_t t[12], borrow;
+  ptx_sub_cc(t[0], r.v[0], fp_modw(0));
+#pragma unroll
+  for (int k = 1; k < 12; k++) ptx_subc_cc(t[k], r.v[k], fp_modw(k));
+  ptx_subc(borrow, 0u, 0u);
+#pragma unroll
+  for (int k = 0; k < 12; k++) r.v[k] = borrow ? r.v[k] : t[k];
+  return r;
+}
+// a - b mod p  (same value as src/fp.rs:421-423, which computes neg(b) + a)
+B200_DEV fp fp_sub(const fp &a, const fp &b) {
+  fp r;
+  uint32_t borrow;
+  ptx_sub_cc(r.v[0], a.v[0], b.v[0]);
+#pragma unroll
+  for (int k = 1; k < 12; k++) ptx_subc_cc(r.v[k], a.v[k], b.v[k]);
+  ptx_subc(borrow, 0u, 0u);  // 0xffffffff when a < b
+  ptx_add_cc(r.v[0], r.v[0], fp_modw(0) & borrow);
+#pragma unroll
+  for (int k = 1; k < 11; k++) ptx_addc_cc(r.v[k], r.v[k], fp_modw(k) & borrow);
+  ptx_addc(r.v[11], r.v[11], fp_modw(11) & borrow);
+  return r;
+}
+B200_DEV bool fp_is_zero(const fp &a) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int k = 0; k < 12; k++) o |= a.v[k];
+  return o == 0;
+}
+B200_DEV bool fp_eq(const fp &a, const fp &b) {
+  uint32_t o = 0;
+#pragma unroll
+  for (int k = 0; k < 12; k++) o |= a.v[k] ^ b.v[k];
+  return o == 0;
+}
+// src/fp.rs:396-418
+B200_DEV fp fp_neg(const fp &a) {
+  fp r;
+  uint32_t mask = fp_is_zero(a) ? 0u : 0xffffffffu;
+  ptx_sub_cc(r.v[0], fp_modw(0), a.v[0]);
+#pragma unroll
+  for (int k = 1; k < 11; k++) ptx_subc_cc(r.v[k], fp_modw(k), a.v[k]);
+  ptx_subc(r.v[11], fp_modw(11), a.v[11]);
+#pragma unroll
+  for (int k = 0; k < 12; k++) r.v[k] &= mask;
+  return r;
+}
+B200_DEV fp fp_dbl(const fp &a) { return fp_add(a, a); }
+B200_DEV fp fp_select(const fp &a, const fp &b, bool choose_b) {
+  fp r;
+#pragma unroll
+  for (int k = 0; k < 12; k++) r.v[k] = choose_b ? b.v[k] : a.v[k];
+  return r;
+}
+
+// a^(p-2)  (src/fp.rs:346-358 via pow_vartime :309-321: 384 squarings, multiply on set bits, MSB first)
+B200_DEV fp fp_inv(const fp &a) {
+  fp res = fp_one();
+#pragma unroll 1
+  for (int w = 11; w >= 0; w--) {
+    uint32_t e = FP_MOD[w] - (w == 0 ? 2u : 0u);  // p - 2 : low word 0xffffaaab - 2, no borrow
+#pragma unroll 1
+    for (int i = 31; i >= 0; i--) {
+      res = fp_sqr(res);
+      if ((e >> i) & 1) res = fp_mul(res, a);
+    }
+  }
+  return res;
+}
+
+// ---- global memory <-> registers.  Memory layout = the reference's Fp([u64;6]) little-endian limbs,
+// i.e. 12 consecutive little-endian 32-bit words, 16-byte aligned groups -> three 128-bit accesses.
+B200_DEV fp fp_load(const void *p) {
+  const uint4 *q = reinterpret_cast<const uint4 *>(p);
+  uint4 a = q[0], b = q[1], c = q[2];
+  fp r = {{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w}};
+  return r;
+}
+B200_DEV void fp_store(void *p, const fp &r) {
+  uint4 *q = reinterpret_cast<uint4 *>(p);
+  q[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  q[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+  q[2] = make_uint4(r.v[8], r.v[9], r.v[10], r.v[11]);
+}
+B200_DEV fp fp_load_ro(const void *p) {
+  const uint4 *q = reinterpret_cast<const uint4 *>(p);
+  uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+  fp r = {{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w}};
+  return r;
+}
+
+}  // namespace b200

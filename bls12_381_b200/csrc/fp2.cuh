@@ -1,0 +1,138 @@
+// Fp2 = Fp[u]/(u^2+1).  Replaces src/fp2.rs (mul :205, square :182, add/sub/neg :224-243,
+// mul_by_nonresidue :156, conjugate/frobenius :141-153, invert :300).  Values are canonical, hence
+// bit-identical to the reference; the multiplication is 3-mul Karatsuba over the register-resident
+// fp_mul instead of the reference's two interleaved sum_of_products (same field element).
+#pragma once
+#include "fp.cuh"
+
+namespace b200 {
+
+struct fp2 {
+  fp c0, c1;
+};
+
+B200_DEV fp2 fp2_zero() { return fp2{fp_zero(), fp_zero()}; }
+B200_DEV fp2 fp2_one() { return fp2{fp_one(), fp_zero()}; }
+B200_DEV fp2 fp2_add(const fp2 &a, const fp2 &b) { return fp2{fp_add(a.c0, b.c0), fp_add(a.c1, b.c1)}; }
+B200_DEV fp2 fp2_sub(const fp2 &a, const fp2 &b) { return fp2{fp_sub(a.c0, b.c0), fp_sub(a.c1, b.c1)}; }
+B200_DEV fp2 fp2_neg(const fp2 &a) { return fp2{fp_neg(a.c0), fp_neg(a.c1)}; }
+B200_DEV fp2 fp2_dbl(const fp2 &a) { return fp2{fp_dbl(a.c0), fp_dbl(a.c1)}; }
+B200_DEV fp2 fp2_conj(const fp2 &a) { return fp2{a.c0, fp_neg(a.c1)}; }
+B200_DEV bool fp2_is_zero(const fp2 &a) { return fp_is_zero(a.c0) && fp_is_zero(a.c1); }
+B200_DEV bool fp2_eq(const fp2 &a, const fp2 &b) { return fp_eq(a.c0, b.c0) && fp_eq(a.c1, b.c1); }
+// (a + bu)(1 + u) = (a - b) + (a + b)u      (src/fp2.rs:156-166)
+B200_DEV fp2 fp2_mul_by_nonresidue(const fp2 &a) { return fp2{fp_sub(a.c0, a.c1), fp_add(a.c0, a.c1)}; }
+B200_DEV fp2 fp2_mul(const fp2 &a, const fp2 &b) {
+  fp t0 = fp_mul(a.c0, b.c0);
+  fp t1 = fp_mul(a.c1, b.c1);
+  fp s = fp_mul(fp_add(a.c0, a.c1), fp_add(b.c0, b.c1));
+  return fp2{fp_sub(t0, t1), fp_sub(fp_sub(s, t0), t1)};
+}
+// complex squaring (src/fp2.rs:182-203)
+B200_DEV fp2 fp2_sqr(const fp2 &a) {
+  fp s = fp_add(a.c0, a.c1), d = fp_sub(a.c0, a.c1), t = fp_dbl(a.c0);
+  return fp2{fp_mul(s, d), fp_mul(t, a.c1)};
+}
+B200_DEV fp2 fp2_mul_fp(const fp2 &a, const fp &k) { return fp2{fp_mul(a.c0, k), fp_mul(a.c1, k)}; }
+// src/fp2.rs:300-320 ; returns 0 for 0 (== CtOption::unwrap_or(zero) at the call sites)
+B200_DEV fp2 fp2_inv(const fp2 &a) {
+  fp t = fp_inv(fp_add(fp_sqr(a.c0), fp_sqr(a.c1)));
+  return fp2{fp_mul(a.c0, t), fp_mul(a.c1, fp_neg(t))};
+}
+B200_DEV fp2 fp2_select(const fp2 &a, const fp2 &b, bool choose_b) {
+  return fp2{fp_select(a.c0, b.c0, choose_b), fp_select(a.c1, b.c1, choose_b)};
+}
+B200_DEV fp2 fp2_load(const void *p) {
+  const char *q = reinterpret_cast<const char *>(p);
+  return fp2{fp_load(q), fp_load(q + 48)};
+}
+B200_DEV fp2 fp2_load_ro(const void *p) {
+  const char *q = reinterpret_cast<const char *>(p);
+  return fp2{fp_load_ro(q), fp_load_ro(q + 48)};
+}
+B200_DEV void fp2_store(void *p, const fp2 &a) {
+  char *q = reinterpret_cast<char *>(p);
+  fp_store(q, a.c0);
+  fp_store(q + 48, a.c1);
+}
+
+// Non-inlined Fp2 mul/sqr: ONE copy of the 3x(305-IMAD) body per kernel instead of one per call site.
+// Everything at Fp2 level and above (G2, Fp6, Fp12, pairing) goes through these: the operands do not
+// fit in registers next to a G2 point anyway, and the instruction cache (and ptxas) stay sane.
+#define B200_NOINL static __device__ __noinline__
+B200_NOINL void fp2_mul_ni(fp2 *r, const fp2 *a, const fp2 *b) { *r = fp2_mul(*a, *b); }
+B200_NOINL void fp2_sqr_ni(fp2 *r, const fp2 *a) { *r = fp2_sqr(*a); }
+B200_NOINL void fp_mul_ni(fp *r, const fp *a, const fp *b) { *r = fp_mul(*a, *b); }
+B200_NOINL void fp_inv_ni(fp *r, const fp *a) { *r = fp_inv(*a); }
+B200_DEV fp2 M2(const fp2 &a, const fp2 &b) {
+  fp2 r;
+  fp2_mul_ni(&r, &a, &b);
+  return r;
+}
+B200_DEV fp2 S2(const fp2 &a) {
+  fp2 r;
+  fp2_sqr_ni(&r, &a);
+  return r;
+}
+B200_DEV fp2 fp2_inv_ni(const fp2 &a) {
+  fp n = fp_add(fp_sqr(a.c0), fp_sqr(a.c1)), t;
+  fp_inv_ni(&t, &n);
+  fp nt = fp_neg(t), r0, r1;
+  fp_mul_ni(&r0, &a.c0, &t);
+  fp_mul_ni(&r1, &a.c1, &nt);
+  return fp2{r0, r1};
+}
+
+// ---- uniform names so the curve templates (curve.cuh) work over Fp (G1) and Fp2 (G2)
+B200_DEV fp f_add(const fp &a, const fp &b) { return fp_add(a, b); }
+B200_DEV fp f_sub(const fp &a, const fp &b) { return fp_sub(a, b); }
+B200_DEV fp f_mul(const fp &a, const fp &b) { return fp_mul(a, b); }
+B200_DEV fp f_sqr(const fp &a) { return fp_sqr(a); }
+B200_DEV fp f_neg(const fp &a) { return fp_neg(a); }
+B200_DEV fp f_dbl(const fp &a) { return fp_dbl(a); }
+B200_DEV fp f_inv(const fp &a) { return fp_inv(a); }
+B200_DEV bool f_is_zero(const fp &a) { return fp_is_zero(a); }
+B200_DEV bool f_eq(const fp &a, const fp &b) { return fp_eq(a, b); }
+B200_DEV fp f_select(const fp &a, const fp &b, bool c) { return fp_select(a, b, c); }
+B200_DEV void f_store(void *p, const fp &a) { fp_store(p, a); }
+B200_DEV fp2 f_add(const fp2 &a, const fp2 &b) { return fp2_add(a, b); }
+B200_DEV fp2 f_sub(const fp2 &a, const fp2 &b) { return fp2_sub(a, b); }
+B200_DEV fp2 f_mul(const fp2 &a, const fp2 &b) { return M2(a, b); }
+B200_DEV fp2 f_sqr(const fp2 &a) { return S2(a); }
+B200_DEV fp2 f_neg(const fp2 &a) { return fp2_neg(a); }
+B200_DEV fp2 f_dbl(const fp2 &a) { return fp2_dbl(a); }
+B200_DEV fp2 f_inv(const fp2 &a) { return fp2_inv_ni(a); }
+B200_DEV bool f_is_zero(const fp2 &a) { return fp2_is_zero(a); }
+B200_DEV bool f_eq(const fp2 &a, const fp2 &b) { return fp2_eq(a, b); }
+B200_DEV fp2 f_select(const fp2 &a, const fp2 &b, bool c) { return fp2_select(a, b, c); }
+B200_DEV void f_store(void *p, const fp2 &a) { fp2_store(p, a); }
+
+template <class F> struct field_traits;
+template <> struct field_traits<fp> {
+  static constexpr int bytes = 48;
+  static B200_DEV fp zero() { return fp_zero(); }
+  static B200_DEV fp one() { return fp_one(); }
+  static B200_DEV fp load(const void *p) { return fp_load(p); }
+  static B200_DEV fp load_ro(const void *p) { return fp_load_ro(p); }
+  // 3b = 12 for E: y^2 = x^3 + 4   (src/g1.rs:597-601 computes the same by repeated adds)
+  static B200_DEV fp mul_by_3b(const fp &a) {
+    fp t = fp_dbl(fp_dbl(a));       // 4a
+    return fp_add(fp_dbl(t), t);    // 12a
+  }
+};
+template <> struct field_traits<fp2> {
+  static constexpr int bytes = 96;
+  static B200_DEV fp2 zero() { return fp2_zero(); }
+  static B200_DEV fp2 one() { return fp2_one(); }
+  static B200_DEV fp2 load(const void *p) { return fp2_load(p); }
+  static B200_DEV fp2 load_ro(const void *p) { return fp2_load_ro(p); }
+  // 3b' = 12(1+u) for E': y^2 = x^3 + 4(1+u).  The reference multiplies by the constant B3 with a
+  // full Fp2 mul (src/g2.rs:650-652); the same canonical element is 12 * mul_by_nonresidue(a).
+  static B200_DEV fp2 mul_by_3b(const fp2 &a) {
+    fp2 n = fp2_mul_by_nonresidue(a);
+    fp2 t = fp2_dbl(fp2_dbl(n));
+    return fp2_add(fp2_dbl(t), t);
+  }
+};
+
+}  // namespace b200

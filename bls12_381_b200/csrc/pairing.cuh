@@ -1,0 +1,218 @@
+// Optimal-ate Miller loop and final exponentiation on the device, one thread per pairing.
+// Replaces src/pairings.rs: miller_loop :668-694, doubling_step :709-738, addition_step :740-770,
+// ell :696-707, pairing() identity handling :636-651, final_exponentiation :48-176 (fp4_square :50,
+// cyclotomic_square :66, cycolotomic_exp :115).  The step formulas and the exponentiation chain follow
+// the reference sequence, so MillerLoopResult limbs (not only Gt) are bit-identical.
+#pragma once
+#include "curve.cuh"
+#include "tower.cuh"
+
+namespace b200 {
+
+#define B200_BLS_X 0xd201000000010000ull  // src/lib.rs:72 ; BLS_X_IS_NEGATIVE = true (:74)
+
+struct line_coeffs {
+  fp2 a, b, c;
+};
+
+// src/pairings.rs:709-738
+B200_NOINL void pairing_doubling_step(proj<fp2> *r, line_coeffs *out) {
+  fp2 tmp0 = S2(r->x);
+  fp2 tmp1 = S2(r->y);
+  fp2 tmp2 = S2(tmp1);
+  fp2 tmp3 = fp2_sub(fp2_sub(S2(fp2_add(tmp1, r->x)), tmp0), tmp2);
+  tmp3 = fp2_dbl(tmp3);
+  fp2 tmp4 = fp2_add(fp2_dbl(tmp0), tmp0);
+  fp2 tmp6 = fp2_add(r->x, tmp4);
+  fp2 tmp5 = S2(tmp4);
+  fp2 zsquared = S2(r->z);
+  r->x = fp2_sub(fp2_sub(tmp5, tmp3), tmp3);
+  r->z = fp2_sub(fp2_sub(S2(fp2_add(r->z, r->y)), tmp1), zsquared);
+  r->y = M2(fp2_sub(tmp3, r->x), tmp4);
+  tmp2 = fp2_dbl(tmp2);
+  tmp2 = fp2_dbl(tmp2);
+  tmp2 = fp2_dbl(tmp2);
+  r->y = fp2_sub(r->y, tmp2);
+  tmp3 = M2(tmp4, zsquared);
+  tmp3 = fp2_dbl(tmp3);
+  tmp3 = fp2_neg(tmp3);
+  tmp6 = fp2_sub(fp2_sub(S2(tmp6), tmp0), tmp5);
+  tmp1 = fp2_dbl(tmp1);
+  tmp1 = fp2_dbl(tmp1);
+  tmp6 = fp2_sub(tmp6, tmp1);
+  tmp0 = M2(r->z, zsquared);
+  tmp0 = fp2_dbl(tmp0);
+  out->a = tmp0;
+  out->b = tmp3;
+  out->c = tmp6;
+}
+// src/pairings.rs:740-770
+B200_NOINL void pairing_addition_step(proj<fp2> *r, const fp2 *qx, const fp2 *qy, line_coeffs *out) {
+  fp2 zsquared = S2(r->z);
+  fp2 ysquared = S2(*qy);
+  fp2 t0 = M2(zsquared, *qx);
+  fp2 t1 = M2(fp2_sub(fp2_sub(S2(fp2_add(*qy, r->z)), ysquared), zsquared), zsquared);
+  fp2 t2 = fp2_sub(t0, r->x);
+  fp2 t3 = S2(t2);
+  fp2 t4 = fp2_dbl(t3);
+  t4 = fp2_dbl(t4);
+  fp2 t5 = M2(t4, t2);
+  fp2 t6 = fp2_sub(fp2_sub(t1, r->y), r->y);
+  fp2 t9 = M2(t6, *qx);
+  fp2 t7 = M2(t4, r->x);
+  r->x = fp2_sub(fp2_sub(fp2_sub(S2(t6), t5), t7), t7);
+  r->z = fp2_sub(fp2_sub(S2(fp2_add(r->z, t2)), zsquared), t3);
+  fp2 t10 = fp2_add(*qy, r->z);
+  fp2 t8 = M2(fp2_sub(t7, r->x), t6);
+  t0 = M2(r->y, t5);
+  t0 = fp2_dbl(t0);
+  r->y = fp2_sub(t8, t0);
+  t10 = fp2_sub(S2(t10), ysquared);
+  fp2 ztsquared = S2(r->z);
+  t10 = fp2_sub(t10, ztsquared);
+  t9 = fp2_sub(fp2_dbl(t9), t10);
+  t10 = fp2_dbl(r->z);
+  t6 = fp2_neg(t6);
+  t1 = fp2_dbl(t6);
+  out->a = t10;
+  out->b = t1;
+  out->c = t9;
+}
+// src/pairings.rs:696-707 : f = f.mul_by_014(coeffs.2, coeffs.1 * p.x, coeffs.0 * p.y)
+B200_DEV void pairing_ell(fp12 *f, const line_coeffs *co, const fp *px, const fp *py) {
+  fp2 c0, c1;
+  fp_mul_ni(&c0.c0, &co->a.c0, py);
+  fp_mul_ni(&c0.c1, &co->a.c1, py);
+  fp_mul_ni(&c1.c0, &co->b.c0, px);
+  fp_mul_ni(&c1.c1, &co->b.c1, px);
+  fp12_mul_by_014(f, f, &co->c, &c1, &c0);
+}
+
+// Miller loop of one (P, Q) pair, exactly the schedule of src/pairings.rs:668-694 as driven by
+// pairing() :607-646.  `either_identity` => the generators are substituted and the result is one().
+B200_DEV void miller_loop_pair(fp12 *f, const affine<fp> &pin, const affine<fp2> &qin) {
+  bool either = pin.inf || qin.inf;
+  fp px = either ? fp_const(K_G1_GEN_X) : pin.x;
+  fp py = either ? fp_const(K_G1_GEN_Y) : pin.y;
+  fp2 qx = either ? fp2{fp_const(K_G2_GEN_X0), fp_const(K_G2_GEN_X1)} : qin.x;
+  fp2 qy = either ? fp2{fp_const(K_G2_GEN_Y0), fp_const(K_G2_GEN_Y1)} : qin.y;
+  proj<fp2> cur{qx, qy, fp2_one()};
+  line_coeffs co;
+  fp12_set_one(f);
+  const unsigned long long x = B200_BLS_X >> 1;
+  bool found_one = false;
+#pragma unroll 1
+  for (int b = 63; b >= 0; b--) {
+    bool bit = (x >> b) & 1;
+    if (!found_one) {
+      found_one = bit;
+      continue;
+    }
+    pairing_doubling_step(&cur, &co);
+    pairing_ell(f, &co, &px, &py);
+    if (bit) {
+      pairing_addition_step(&cur, &qx, &qy, &co);
+      pairing_ell(f, &co, &px, &py);
+    }
+    fp12_sqr(f, f);
+  }
+  pairing_doubling_step(&cur, &co);
+  pairing_ell(f, &co, &px, &py);
+  fp12_conj(f, f);  // BLS_X_IS_NEGATIVE
+  if (either) fp12_set_one(f);
+}
+
+// src/pairings.rs:50-62
+B200_DEV void fp4_square(fp2 *c0, fp2 *c1, const fp2 &a, const fp2 &b) {
+  fp2 t0 = S2(a), t1 = S2(b);
+  fp2 t2 = fp2_mul_by_nonresidue(t1);
+  *c0 = fp2_add(t2, t0);
+  t2 = fp2_add(a, b);
+  t2 = S2(t2);
+  t2 = fp2_sub(t2, t0);
+  *c1 = fp2_sub(t2, t1);
+}
+// src/pairings.rs:66-113  (r may alias f)
+B200_NOINL void cyclotomic_square(fp12 *r, const fp12 *f) {
+  fp2 z0 = f->c0.c0, z4 = f->c0.c1, z3 = f->c0.c2, z2 = f->c1.c0, z1 = f->c1.c1, z5 = f->c1.c2;
+  fp2 t0, t1, t2, t3;
+  fp4_square(&t0, &t1, z0, z1);
+  z0 = fp2_sub(t0, z0);
+  z0 = fp2_add(fp2_dbl(z0), t0);
+  z1 = fp2_add(t1, z1);
+  z1 = fp2_add(fp2_dbl(z1), t1);
+  fp4_square(&t0, &t1, z2, z3);
+  fp4_square(&t2, &t3, z4, z5);
+  z4 = fp2_sub(t0, z4);
+  z4 = fp2_add(fp2_dbl(z4), t0);
+  z5 = fp2_add(t1, z5);
+  z5 = fp2_add(fp2_dbl(z5), t1);
+  t0 = fp2_mul_by_nonresidue(t3);
+  z2 = fp2_add(t0, z2);
+  z2 = fp2_add(fp2_dbl(z2), t0);
+  z3 = fp2_sub(t2, z3);
+  z3 = fp2_add(fp2_dbl(z3), t2);
+  r->c0.c0 = z0;
+  r->c0.c1 = z4;
+  r->c0.c2 = z3;
+  r->c1.c0 = z2;
+  r->c1.c1 = z1;
+  r->c1.c2 = z5;
+}
+// src/pairings.rs:115-132  (r must not alias f)
+B200_NOINL void cyclotomic_exp(fp12 *r, const fp12 *f) {
+  fp12_set_one(r);
+  bool found_one = false;
+#pragma unroll 1
+  for (int b = 63; b >= 0; b--) {
+    bool bit = (B200_BLS_X >> b) & 1;
+    if (found_one)
+      cyclotomic_square(r, r);
+    else
+      found_one = bit;
+    if (bit) fp12_mul(r, r, f);
+  }
+  fp12_conj(r, r);
+}
+// src/pairings.rs:134-176   (in place)
+B200_DEV void final_exponentiation(fp12 *f) {
+  fp12 t0, t1, t2, t3, t4, t5, t6;
+  t0 = *f;
+#pragma unroll 1
+  for (int i = 0; i < 6; i++) fp12_frobenius(&t0, &t0);
+  fp12_inv(&t1, f);
+  fp12_mul(&t2, &t0, &t1);
+  t1 = t2;
+  fp12_frobenius(&t2, &t2);
+  fp12_frobenius(&t2, &t2);
+  fp12_mul(&t2, &t2, &t1);
+  cyclotomic_square(&t1, &t2);
+  fp12_conj(&t1, &t1);
+  cyclotomic_exp(&t3, &t2);
+  cyclotomic_square(&t4, &t3);
+  fp12_mul(&t5, &t1, &t3);
+  cyclotomic_exp(&t1, &t5);
+  cyclotomic_exp(&t0, &t1);
+  cyclotomic_exp(&t6, &t0);
+  fp12_mul(&t6, &t6, &t4);
+  cyclotomic_exp(&t4, &t6);
+  fp12_conj(&t5, &t5);
+  fp12 tmp;
+  fp12_mul(&tmp, &t5, &t2);
+  fp12_mul(&t4, &t4, &tmp);
+  fp12_conj(&t5, &t2);
+  fp12_mul(&t1, &t1, &t2);
+  fp12_frobenius(&t1, &t1);
+  fp12_frobenius(&t1, &t1);
+  fp12_frobenius(&t1, &t1);
+  fp12_mul(&t6, &t6, &t5);
+  fp12_frobenius(&t6, &t6);
+  fp12_mul(&t3, &t3, &t0);
+  fp12_frobenius(&t3, &t3);
+  fp12_frobenius(&t3, &t3);
+  fp12_mul(&t3, &t3, &t1);
+  fp12_mul(&t3, &t3, &t6);
+  fp12_mul(f, &t3, &t4);
+}
+
+}  // namespace b200

@@ -1,0 +1,211 @@
+"""Host-side harness over the C ABI (include/bls12381_b200.h).
+
+The reference is a Rust crate; its drop-in host shim is the Rust `-sys` binding shown in INTEGRATION.md
+and the C++ mirror in bls12_381_b200/host/bls12_381.hpp.  This module is the Python face of the same
+ABI used by tests/ and bench.py.  Method names follow the reference functions they batch:
+`g1_mul_batch` = G1Projective * Scalar (src/g1.rs:556), `g1_msm` = sum_i p_i*s_i (:573, :161),
+`batch_normalize` (:806), `pairing_batch` = pairing() (src/pairings.rs:607), `multi_miller_loop` (:554),
+`final_exponentiation_batch` (:48).
+
+Arrays: numpy uint64 limbs / uint8 flags+scalars for the host-pointer entry points; torch CUDA tensors
+(any dtype, contiguous, byte-exact layout) for the `_dev` entry points, which run on the engine's own
+stream and return after synchronising it.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+OPS = dict(mul=0, add=1, sub=2, square=3, neg=4, invert=5, frobenius=6, conjugate=7, mul_by_nonresidue=8,
+           cyclotomic_square=9)
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+def _np(a, dtype, width=None):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    return a if width is None else a.reshape(-1, width)
+
+
+def _hp(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _dp(t):
+    """device pointer of a torch CUDA tensor (or None)"""
+    if t is None:
+        return None
+    if not t.is_cuda or not t.is_contiguous():
+        raise ValueError("expected a contiguous CUDA tensor")
+    return C.c_void_p(t.data_ptr())
+
+
+class Engine:
+    """One b200_ctx = one GPU + one stream + scratch memory."""
+
+    AFF = {1: 12, 2: 24}
+    PROJ = {1: 18, 2: 36}
+
+    def __init__(self, device=-1):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        rc = self.lib.b200_ctx_create(int(device), C.byref(h))
+        if rc != 0:
+            raise B200Error("b200_ctx_create: %s" % self.lib.b200_strerror(rc).decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b200_ctx_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise B200Error("%s: %s (%s)" % (what, self.lib.b200_strerror(rc).decode(),
+                                             self.lib.b200_last_error(self.h).decode()))
+
+    @property
+    def device(self):
+        return self.lib.b200_ctx_device(self.h)
+
+    @property
+    def stream(self):
+        return self.lib.b200_ctx_stream(self.h)
+
+    @property
+    def launches(self):
+        return int(self.lib.b200_ctx_launch_count(self.h))
+
+    def set_msm_window(self, c):
+        return self.lib.b200_ctx_set_msm_window(self.h, int(c))
+
+    def imad_peak(self, iters=2000):
+        v, ms = C.c_double(), C.c_double()
+        self._ck(self.lib.b200_imad_peak(self.h, iters, C.byref(v), C.byref(ms)), "imad_peak")
+        return v.value, ms.value
+
+    # ---------------------------------------------------------------- field tower (parity surface)
+    def tower(self, level, op, a, b=None):
+        w = 6 * level
+        a = _np(a, np.uint64, w)
+        b = None if b is None else _np(b, np.uint64, w)
+        out = np.empty_like(a)
+        self._ck(self.lib.b200_tower_op(self.h, level, OPS[op], _hp(a), _hp(b), _hp(out), a.shape[0]), "tower_op")
+        return out
+
+    # ---------------------------------------------------------------- groups, host pointers
+    def _g(self, k):
+        return "b200_g%d_" % k
+
+    def mul_batch(self, k, p, s):
+        p, s = _np(p, np.uint64, self.PROJ[k]), _np(s, np.uint8, 32)
+        out = np.empty_like(p)
+        self._ck(getattr(self.lib, self._g(k) + "mul_batch")(self.h, _hp(p), _hp(s), p.shape[0], _hp(out)), "mul_batch")
+        return out
+
+    def double_batch(self, k, p):
+        p = _np(p, np.uint64, self.PROJ[k])
+        out = np.empty_like(p)
+        self._ck(getattr(self.lib, self._g(k) + "double_batch")(self.h, _hp(p), p.shape[0], _hp(out)), "double_batch")
+        return out
+
+    def add_batch(self, k, p, q):
+        p, q = _np(p, np.uint64, self.PROJ[k]), _np(q, np.uint64, self.PROJ[k])
+        out = np.empty_like(p)
+        self._ck(getattr(self.lib, self._g(k) + "add_batch")(self.h, _hp(p), _hp(q), p.shape[0], _hp(out)), "add_batch")
+        return out
+
+    def add_mixed_batch(self, k, p, qxy, qinf=None):
+        p, qxy = _np(p, np.uint64, self.PROJ[k]), _np(qxy, np.uint64, self.AFF[k])
+        qinf = None if qinf is None else _np(qinf, np.uint8)
+        out = np.empty_like(p)
+        self._ck(getattr(self.lib, self._g(k) + "add_mixed_batch")(self.h, _hp(p), _hp(qxy), _hp(qinf), p.shape[0],
+                                                                   _hp(out)), "add_mixed_batch")
+        return out
+
+    def batch_normalize(self, k, p):
+        p = _np(p, np.uint64, self.PROJ[k])
+        xy = np.empty((p.shape[0], self.AFF[k]), np.uint64)
+        inf = np.empty(p.shape[0], np.uint8)
+        self._ck(getattr(self.lib, self._g(k) + "batch_normalize")(self.h, _hp(p), p.shape[0], _hp(xy), _hp(inf)),
+                 "batch_normalize")
+        return xy, inf
+
+    def msm(self, k, xy, inf, s):
+        xy, s = _np(xy, np.uint64, self.AFF[k]), _np(s, np.uint8, 32)
+        if xy.shape[0] != s.shape[0]:
+            raise ValueError("points/scalars length mismatch")     # the reference's zip() would truncate
+        inf = None if inf is None else _np(inf, np.uint8)
+        out = np.empty((1, self.PROJ[k]), np.uint64)
+        self._ck(getattr(self.lib, self._g(k) + "msm")(self.h, _hp(xy), _hp(inf), _hp(s), xy.shape[0], _hp(out)), "msm")
+        return out
+
+    # ---------------------------------------------------------------- pairings, host pointers
+    def _pairs(self, pxy, pinf, qxy, qinf):
+        pxy, qxy = _np(pxy, np.uint64, 12), _np(qxy, np.uint64, 24)
+        if pxy.shape[0] != qxy.shape[0]:
+            raise ValueError("p/q length mismatch")
+        pinf = None if pinf is None else _np(pinf, np.uint8)
+        qinf = None if qinf is None else _np(qinf, np.uint8)
+        return pxy, pinf, qxy, qinf
+
+    def miller_loop_batch(self, pxy, pinf, qxy, qinf):
+        pxy, pinf, qxy, qinf = self._pairs(pxy, pinf, qxy, qinf)
+        out = np.empty((pxy.shape[0], 72), np.uint64)
+        self._ck(self.lib.b200_miller_loop_batch(self.h, _hp(pxy), _hp(pinf), _hp(qxy), _hp(qinf), pxy.shape[0],
+                                                 _hp(out)), "miller_loop_batch")
+        return out
+
+    def final_exponentiation_batch(self, f):
+        f = _np(f, np.uint64, 72)
+        out = np.empty_like(f)
+        self._ck(self.lib.b200_final_exponentiation_batch(self.h, _hp(f), f.shape[0], _hp(out)), "final_exp")
+        return out
+
+    def pairing_batch(self, pxy, pinf, qxy, qinf):
+        pxy, pinf, qxy, qinf = self._pairs(pxy, pinf, qxy, qinf)
+        out = np.empty((pxy.shape[0], 72), np.uint64)
+        self._ck(self.lib.b200_pairing_batch(self.h, _hp(pxy), _hp(pinf), _hp(qxy), _hp(qinf), pxy.shape[0], _hp(out)),
+                 "pairing_batch")
+        return out
+
+    def multi_miller_loop(self, pxy, pinf, qxy, qinf):
+        pxy, pinf, qxy, qinf = self._pairs(pxy, pinf, qxy, qinf)
+        out = np.empty((1, 72), np.uint64)
+        self._ck(self.lib.b200_multi_miller_loop(self.h, _hp(pxy), _hp(pinf), _hp(qxy), _hp(qinf), pxy.shape[0],
+                                                 _hp(out)), "multi_miller_loop")
+        return out
+
+    # ---------------------------------------------------------------- device-pointer entry points (torch tensors)
+    def mul_batch_dev(self, k, p, s, out, n):
+        self._ck(getattr(self.lib, self._g(k) + "mul_batch_dev")(self.h, _dp(p), _dp(s), n, _dp(out)), "mul_batch_dev")
+
+    def batch_normalize_dev(self, k, p, n, out_xy, out_inf):
+        self._ck(getattr(self.lib, self._g(k) + "batch_normalize_dev")(self.h, _dp(p), n, _dp(out_xy), _dp(out_inf)),
+                 "batch_normalize_dev")
+
+    def msm_dev(self, k, xy, inf, s, n, out, shard=0, n_shards=1):
+        self._ck(getattr(self.lib, self._g(k) + "msm_shard_dev")(self.h, _dp(xy), _dp(inf), _dp(s), n, shard, n_shards,
+                                                                 _dp(out)), "msm_dev")
+
+    def sum_dev(self, k, parts, n, out):
+        self._ck(getattr(self.lib, self._g(k) + "sum_dev")(self.h, _dp(parts), n, _dp(out)), "sum_dev")
+
+    def miller_loop_batch_dev(self, p, pinf, q, qinf, n, out):
+        self._ck(self.lib.b200_miller_loop_batch_dev(self.h, _dp(p), _dp(pinf), _dp(q), _dp(qinf), n, _dp(out)),
+                 "miller_loop_batch_dev")
+
+    def final_exponentiation_batch_dev(self, f, n, out):
+        self._ck(self.lib.b200_final_exponentiation_batch_dev(self.h, _dp(f), n, _dp(out)), "final_exp_dev")
+
+    def pairing_batch_dev(self, p, pinf, q, qinf, n, out):
+        self._ck(self.lib.b200_pairing_batch_dev(self.h, _dp(p), _dp(pinf), _dp(q), _dp(qinf), n, _dp(out)),
+                 "pairing_batch_dev")
+
+    def fp12_product_dev(self, f, n, out):
+        self._ck(self.lib.b200_fp12_product_dev(self.h, _dp(f), n, _dp(out)), "fp12_product_dev")

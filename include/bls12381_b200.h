@@ -1,0 +1,144 @@
+/* bls12381_b200 — C ABI of the B200-native BLS12-381 hot path (libbls12381_b200.so).
+ *
+ * This is the drop-in boundary for the data-parallel hot path of zkcrypto/bls12_381 v0.8.0
+ * (SURVEY.md §8b): batched scalar multiplication, G1/G2 multi-scalar multiplication, batched
+ * multi_miller_loop / final_exponentiation / pairing, and batch_normalize.  The reference crate has
+ * no FFI of its own (#![deny(unsafe_code)], src/lib.rs:17); each entry point below names the
+ * reference function it replaces, and INTEGRATION.md shows the Rust `-sys` binding that calls it.
+ *
+ * Data layouts mirror the reference's in-memory values exactly (all little-endian):
+ *   Fp     = Fp([u64;6])   Montgomery form, R = 2^384, canonical (< p)          src/fp.rs:15
+ *   Fp2    = {c0, c1}                                                           src/fp2.rs:11
+ *   Fp12   = 12 Fp in the order c0.c0.c0, c0.c0.c1, c0.c1.c0, ... c1.c2.c1      src/fp12.rs:13
+ *   scalar = Scalar::to_bytes(): canonical 32-byte little-endian integer < q    src/scalar.rs:284
+ * Affine points are passed as coordinate arrays plus an optional infinity-flag array (one byte per
+ * point, non-zero = identity; NULL = no identities).  A set flag means G*Affine::identity()
+ * (x = 0, y = 1) whatever the coordinate bytes hold.  Rust structs are not repr(C), so the Rust shim
+ * marshals field by field into these layouts.
+ *
+ * Conventions: every function returns 0 on success or a negative B200_E* code; nothing aborts,
+ * throws or longjmps across the boundary.  The caller owns all buffers; the library keeps no pointer
+ * after return.  A b200_ctx owns one CUDA device, one stream and grow-only scratch memory; calls on
+ * one ctx are serialised by an internal mutex, distinct ctxs are independent (Send + Sync on the Rust
+ * side).  Functions without a suffix take HOST pointers (copies included); `_dev` variants take
+ * DEVICE pointers on the ctx's device, enqueue on the ctx stream and synchronise it before returning
+ * unless stated otherwise.  No CPU fallback exists: without a usable CUDA device every call fails
+ * with B200_ENODEV.
+ */
+#ifndef BLS12381_B200_H
+#define BLS12381_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { uint64_t l[6]; } b200_fp;                 /* 48 B  */
+typedef struct { b200_fp c0, c1; } b200_fp2;               /* 96 B  */
+typedef struct { b200_fp c[12]; } b200_fp12;               /* 576 B: Gt / MillerLoopResult */
+typedef struct { b200_fp x, y; } b200_g1_affine;           /* 96 B  G1Affine coords   src/g1.rs:28  */
+typedef struct { b200_fp x, y, z; } b200_g1_projective;    /* 144 B G1Projective      src/g1.rs:442 */
+typedef struct { b200_fp2 x, y; } b200_g2_affine;          /* 192 B G2Affine coords   src/g2.rs:29  */
+typedef struct { b200_fp2 x, y, z; } b200_g2_projective;   /* 288 B G2Projective      src/g2.rs:495 */
+typedef struct { uint8_t b[32]; } b200_scalar;             /* Scalar::to_bytes()      src/scalar.rs:284 */
+
+typedef struct b200_ctx b200_ctx;
+
+enum {
+  B200_OK = 0,
+  B200_EINVAL = -1,  /* NULL pointer / bad size / bad op */
+  B200_ENODEV = -2,  /* no usable CUDA device */
+  B200_ECUDA = -3,   /* CUDA runtime error (see b200_last_error) */
+  B200_ENOMEM = -4
+};
+
+/* ---- context ------------------------------------------------------------------------------- */
+int b200_ctx_create(int device /* CUDA ordinal, -1 = current */, b200_ctx **out);
+void b200_ctx_destroy(b200_ctx *ctx);
+const char *b200_strerror(int code);
+const char *b200_last_error(const b200_ctx *ctx); /* text of the last CUDA error on this ctx */
+int b200_ctx_device(const b200_ctx *ctx);
+/* stream the _dev calls are enqueued on (a cudaStream_t), for callers that time with CUDA events */
+void *b200_ctx_stream(const b200_ctx *ctx);
+/* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
+uint64_t b200_ctx_launch_count(const b200_ctx *ctx);
+/* MSM tuning: window bits c (0 = automatic from n); returns previous value */
+int b200_ctx_set_msm_window(b200_ctx *ctx, int c);
+
+/* ---- field tower, batched (diagnostic / parity surface for src/fp.rs, fp2.rs, fp6.rs, fp12.rs) - */
+/* level: 1 Fp, 2 Fp2, 6 Fp6, 12 Fp12.  op: */
+enum {
+  B200_OP_MUL = 0, B200_OP_ADD = 1, B200_OP_SUB = 2, B200_OP_SQUARE = 3, B200_OP_NEG = 4,
+  B200_OP_INVERT = 5, B200_OP_FROBENIUS = 6, B200_OP_CONJUGATE = 7, B200_OP_MUL_BY_NONRESIDUE = 8,
+  B200_OP_CYCLOTOMIC_SQUARE = 9
+};
+/* out[i] = op(a[i], b[i]); b may be NULL for unary ops; arrays of n elements of 6*level u64 each */
+int b200_tower_op(b200_ctx *ctx, int level, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);
+
+/* ---- G1 ------------------------------------------------------------------------------------- */
+/* out[i] = p[i] * s[i]  — G1Projective::multiply, src/g1.rs:754-774 (via Mul<&Scalar> :556-562).
+ * Raw (x,y,z) limbs are bit-identical to the reference (same complete formulas, same 255 steps). */
+int b200_g1_mul_batch(b200_ctx *ctx, const b200_g1_projective *p, const b200_scalar *s, size_t n, b200_g1_projective *out);
+/* element-wise group ops, limb-exact: double :638, add :670, add_mixed :715 */
+int b200_g1_double_batch(b200_ctx *ctx, const b200_g1_projective *p, size_t n, b200_g1_projective *out);
+int b200_g1_add_batch(b200_ctx *ctx, const b200_g1_projective *p, const b200_g1_projective *q, size_t n, b200_g1_projective *out);
+int b200_g1_add_mixed_batch(b200_ctx *ctx, const b200_g1_projective *p, const b200_g1_affine *q, const uint8_t *q_inf, size_t n, b200_g1_projective *out);
+/* G1Projective::batch_normalize, src/g1.rs:806-839 (same values as per-point G1Affine::from :49-63) */
+int b200_g1_batch_normalize(b200_ctx *ctx, const b200_g1_projective *p, size_t n, b200_g1_affine *out, uint8_t *out_inf);
+/* MSM: out = sum_i points[i] * scalars[i]  — what the reference expresses as
+ * points.zip(scalars).map(|(p,s)| p*s).sum()  (src/g1.rs:573-579, :161-171).  The result is the same
+ * GROUP ELEMENT; it is returned in projective form and is bit-identical after to_affine. */
+int b200_g1_msm(b200_ctx *ctx, const b200_g1_affine *points, const uint8_t *inf /* nullable */, const b200_scalar *scalars, size_t n, b200_g1_projective *out);
+
+/* ---- G2 (same shapes over Fp2; src/g2.rs:825-845, :709, :741, :786, :951-984, :609-615/:162) --- */
+int b200_g2_mul_batch(b200_ctx *ctx, const b200_g2_projective *p, const b200_scalar *s, size_t n, b200_g2_projective *out);
+int b200_g2_double_batch(b200_ctx *ctx, const b200_g2_projective *p, size_t n, b200_g2_projective *out);
+int b200_g2_add_batch(b200_ctx *ctx, const b200_g2_projective *p, const b200_g2_projective *q, size_t n, b200_g2_projective *out);
+int b200_g2_add_mixed_batch(b200_ctx *ctx, const b200_g2_projective *p, const b200_g2_affine *q, const uint8_t *q_inf, size_t n, b200_g2_projective *out);
+int b200_g2_batch_normalize(b200_ctx *ctx, const b200_g2_projective *p, size_t n, b200_g2_affine *out, uint8_t *out_inf);
+int b200_g2_msm(b200_ctx *ctx, const b200_g2_affine *points, const uint8_t *inf, const b200_scalar *scalars, size_t n, b200_g2_projective *out);
+
+/* ---- pairings (src/pairings.rs) ------------------------------------------------------------- */
+/* out[i] = Miller loop of (p[i], q[i]) as in pairing() :607-646 — unprepared, with its identity
+ * handling (either side identity -> Fp12::one()).  MillerLoopResult limbs are bit-identical. */
+int b200_miller_loop_batch(b200_ctx *ctx, const b200_g1_affine *p, const uint8_t *p_inf, const b200_g2_affine *q, const uint8_t *q_inf, size_t n, b200_fp12 *out);
+/* out[i] = MillerLoopResult(in[i]).final_exponentiation()  :48-176  (f^(3(p^12-1)/r)) */
+int b200_final_exponentiation_batch(b200_ctx *ctx, const b200_fp12 *in, size_t n, b200_fp12 *out);
+/* out[i] = pairing(&p[i], &q[i])  :607-653  — n independent Gt values */
+int b200_pairing_batch(b200_ctx *ctx, const b200_g1_affine *p, const uint8_t *p_inf, const b200_g2_affine *q, const uint8_t *q_inf, size_t n, b200_fp12 *gt_out);
+/* out = multi_miller_loop(&[(p_i, G2Prepared::from(q_i))])  :554-603 — ONE MillerLoopResult for the
+ * product; equal as a Gt after final_exponentiation (MillerLoopResult is only defined up to factors
+ * killed by the final exponentiation; this entry multiplies per-pair Miller values). */
+int b200_multi_miller_loop(b200_ctx *ctx, const b200_g1_affine *p, const uint8_t *p_inf, const b200_g2_affine *q, const uint8_t *q_inf, size_t n, b200_fp12 *out);
+
+/* ---- device-pointer variants (inputs already resident in HBM; used by bench.py `value`) ------- */
+int b200_g1_mul_batch_dev(b200_ctx *ctx, const void *p, const void *s, size_t n, void *out);
+int b200_g2_mul_batch_dev(b200_ctx *ctx, const void *p, const void *s, size_t n, void *out);
+int b200_g1_batch_normalize_dev(b200_ctx *ctx, const void *p, size_t n, void *out_xy, void *out_inf);
+int b200_g2_batch_normalize_dev(b200_ctx *ctx, const void *p, size_t n, void *out_xy, void *out_inf);
+int b200_g1_msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scalars, size_t n, void *out);
+int b200_g2_msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scalars, size_t n, void *out);
+/* window-sharded MSM (north_star: "MSM shards by scalar-window across up to 8 GPUs"): processes only
+ * windows w with w % n_shards == shard and writes sum_w 2^(c*w) * S_w for those windows — a partial
+ * group element; the partials of all shards add up (complete add) to the full MSM. */
+int b200_g1_msm_shard_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scalars, size_t n, int shard, int n_shards, void *out);
+int b200_g2_msm_shard_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scalars, size_t n, int shard, int n_shards, void *out);
+/* out = sum_i parts[i] (complete projective adds, src/g1.rs:161-171): combines gathered partials */
+int b200_g1_sum_dev(b200_ctx *ctx, const void *parts, size_t n, void *out);
+int b200_g2_sum_dev(b200_ctx *ctx, const void *parts, size_t n, void *out);
+int b200_miller_loop_batch_dev(b200_ctx *ctx, const void *p, const void *p_inf, const void *q, const void *q_inf, size_t n, void *out);
+int b200_final_exponentiation_batch_dev(b200_ctx *ctx, const void *in, size_t n, void *out);
+int b200_pairing_batch_dev(b200_ctx *ctx, const void *p, const void *p_inf, const void *q, const void *q_inf, size_t n, void *gt_out);
+/* out = product of the n Fp12 values (MillerLoopResult `+`, src/pairings.rs:179-186) */
+int b200_fp12_product_dev(b200_ctx *ctx, const void *in, size_t n, void *out);
+
+/* ---- measurement helper: dependent-free IMAD.WIDE.U32 stream on all SMs; returns achieved
+ * 32x32+64 multiply-adds per second (the integer roofline denominator) ------------ */
+int b200_imad_peak(b200_ctx *ctx, int iters, double *imad_per_sec, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLS12381_B200_H */

@@ -1,0 +1,222 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs — bit-exact (integer work).  Also the reference's own KATs straight on the GPU."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests import pyref, util
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import bls12_381_b200
+    e = bls12_381_b200.Engine()
+    yield e
+    e.close()
+
+
+def eq(a, b):
+    return np.array_equal(np.asarray(a, np.uint64).reshape(-1), np.asarray(b, np.uint64).reshape(-1))
+
+
+# ----------------------------------------------------------------------------- field tower
+@pytest.mark.parametrize("op", ["mul", "add", "sub", "square", "neg", "invert"])
+def test_fp_ops(eng, orc, op):
+    rng = np.random.default_rng(100)
+    e = util.edge_fp()
+    a = np.concatenate([util.rand_fp(rng, 2048), np.repeat(e, len(e), 0)])
+    b = np.concatenate([util.rand_fp(rng, 2048), np.tile(e, (len(e), 1))])
+    if op == "invert":
+        a, b = a[:300], None
+    elif op in ("square", "neg"):
+        b = None
+    got = eng.tower(1, op, a, b)
+    assert eq(got, orc.tower(1, op, a, b))
+
+
+def test_fp_kat_on_gpu(eng):
+    kat = json.load(open(os.path.join(GOLD, "kat.json")))
+    L = lambda k, i: np.array([int(x, 16) for x in kat[k][i]], dtype=np.uint64)
+    k = "fp.rs::test_multiplication"
+    assert eq(eng.tower(1, "mul", L(k, 0), L(k, 1)), L(k, 2))          # src/fp.rs:721-749
+    k = "fp.rs::test_squaring"
+    assert eq(eng.tower(1, "square", L(k, 0)), L(k, 1))                # src/fp.rs:699-719
+    k = "fp.rs::test_inversion"
+    assert eq(eng.tower(1, "invert", L(k, 0)), L(k, 1))                # src/fp.rs:919-940
+    k = "fp2.rs::test_multiplication"
+    c = lambda i: np.concatenate([L(k, i), L(k, i + 1)])
+    assert eq(eng.tower(2, "mul", c(0), c(2)), c(4))                   # src/fp2.rs:464-522
+
+
+@pytest.mark.parametrize("level,ops,n", [
+    (2, ["mul", "add", "sub", "square", "neg", "invert", "frobenius", "conjugate", "mul_by_nonresidue"], 600),
+    (6, ["mul", "add", "sub", "square", "neg", "invert", "frobenius", "mul_by_nonresidue"], 200),
+    (12, ["mul", "square", "invert", "frobenius", "conjugate", "cyclotomic_square"], 100),
+])
+def test_tower_ops(eng, orc, level, ops, n):
+    rng = np.random.default_rng(200 + level)
+    a, b = util.rand_fp(rng, n, level), util.rand_fp(rng, n, level)
+    a[0] = 0
+    a[1, :] = 0
+    a[1, :6] = orc.R_LIMBS
+    for op in ops:
+        bb = b if op in ("mul", "add", "sub") else None
+        aa = a[2:] if op == "invert" else a
+        assert eq(eng.tower(level, op, aa, None if bb is None else bb[:aa.shape[0]]),
+                  orc.tower(level, op, aa, None if bb is None else bb[:aa.shape[0]])), (level, op)
+
+
+# ----------------------------------------------------------------------------- group ops, limb-exact
+@pytest.mark.parametrize("k", [1, 2])
+def test_group_ops(eng, orc, k):
+    rng = np.random.default_rng(300 + k)
+    G = orc.G1 if k == 1 else orc.G2
+    n = 96
+    pr, xy, inf = util.rand_points(orc, k, rng, n)
+    p = util.randomize_z(orc, k, rng, pr)
+    q = np.roll(util.randomize_z(orc, k, rng, pr), 7, 0)
+    # edge cases: identity operands, P + P, P + (-P)
+    ident = G.identity()
+    p[0], q[1] = ident, ident
+    p[2], q[2] = ident, ident
+    q[3] = p[3]
+    neg = p[4].copy()
+    w = 6 * k
+    neg[w:2 * w] = orc.tower(k, "neg", p[4, w:2 * w])
+    q[4] = neg
+    assert eq(eng.double_batch(k, p), G.double(p))
+    assert eq(eng.add_batch(k, p, q), G.add(p, q))
+    qxy, qinf = xy.copy(), inf.copy()
+    qinf[5] = 1
+    qxy[6] = G.to_affine(p[6:7])[0]                       # P + P through the mixed formula
+    assert eq(eng.add_mixed_batch(k, p, qxy, qinf), G.add_mixed(p, qxy, qinf))
+    # batch_normalize, identities included (src/g1.rs:1690-1727)
+    gx, gi = eng.batch_normalize(k, p)
+    ox, oi = G.batch_normalize(p)
+    assert eq(gx, ox) and eq(gi, oi)
+    gx, gi = eng.batch_normalize(k, p[:1])
+    assert gi[0] == 1
+    gx, gi = eng.batch_normalize(k, np.concatenate([p] * 30))
+    assert eq(gx, np.concatenate([ox] * 30)) and eq(gi, np.concatenate([oi] * 30))
+
+
+@pytest.mark.parametrize("k,n", [(1, 1024), (2, 192)])
+def test_mul_batch_config1(eng, orc, k, n):
+    """BASELINE config 1: 1024 x G1Projective * Scalar, raw (x,y,z) limb-exact vs multiply() (src/g1.rs:754)."""
+    rng = np.random.default_rng(400 + k)
+    G = orc.G1 if k == 1 else orc.G2
+    pr, _, _ = util.rand_points(orc, k, rng, n)
+    p = util.randomize_z(orc, k, rng, pr)
+    s = util.rand_scalars(rng, n)
+    s[0] = 0
+    s[1] = util.scalar_bytes(1)
+    s[2] = util.scalar_bytes(pyref.Q - 1)
+    p[3] = G.identity()
+    got = eng.mul_batch(k, p, s)
+    exp = G.mul(p, s, threads=8)
+    assert eq(got, exp)
+
+
+# ----------------------------------------------------------------------------- MSM
+def _msm_case(eng, orc, k, xy, inf, s, cs=(0,)):
+    G = orc.G1 if k == 1 else orc.G2
+    n = xy.shape[0]
+    if n <= 600:
+        exp = G.msm_naive(xy, inf, s, threads=8)
+    else:
+        exp = G.msm_pippenger(xy, inf, s, c=10, threads=8)
+    ea = G.to_affine(exp)
+    for c in cs:
+        eng.set_msm_window(c)
+        got = eng.msm(k, xy, inf, s)
+        ga = G.to_affine(got)
+        assert eq(ga[0], ea[0]) and ga[1][0] == ea[1][0], (k, n, c)
+    eng.set_msm_window(0)
+
+
+@pytest.mark.parametrize("k", [1, 2])
+def test_msm_small_and_edges(eng, orc, k):
+    rng = np.random.default_rng(500 + k)
+    G = orc.G1 if k == 1 else orc.G2
+    _, xy, inf = util.rand_points(orc, k, rng, 300)
+    s = util.rand_scalars(rng, 300)
+    # n = 0 -> identity
+    got = eng.msm(k, xy[:0], None, s[:0])
+    assert G.to_affine(got)[1][0] == 1
+    for n in (1, 2, 3, 37, 300):
+        _msm_case(eng, orc, k, xy[:n], inf[:n], s[:n], cs=(0, 4, 7, 13) if n <= 37 else (0, 9))
+    # edge cases: zero scalars, q-1, identity points, duplicates, P and -P, all-same scalar
+    n = 64
+    xy2, inf2, s2 = xy[:n].copy(), inf[:n].copy(), s[:n].copy()
+    s2[0] = 0
+    s2[1] = util.scalar_bytes(pyref.Q - 1)
+    s2[2] = util.scalar_bytes(1)
+    inf2[3] = 1
+    xy2[5] = xy2[4]
+    s2[5] = s2[4]                                   # duplicate point, same scalar -> same bucket (P + P)
+    xy2[7] = xy2[6]
+    w = 6 * k
+    xy2[7, w:] = orc.tower(k, "neg", xy2[6, w:])
+    s2[7] = s2[6]                                   # P and -P with the same scalar (P + (-P) in a bucket)
+    s2[8:24] = s2[8]                                # all-same scalar
+    _msm_case(eng, orc, k, xy2, inf2, s2, cs=(0, 5, 8, 16))
+    # everything cancels -> identity
+    xy3 = np.concatenate([xy[:8], xy[:8]])
+    xy3[8:, w:] = orc.tower(k, "neg", xy[:8, w:])
+    s3 = np.concatenate([s[:8], s[:8]])
+    got = eng.msm(k, xy3, None, s3)
+    assert G.to_affine(got)[1][0] == 1
+
+
+@pytest.mark.parametrize("k,n", [(1, 5000), (2, 2000)])
+def test_msm_medium(eng, orc, k, n):
+    rng = np.random.default_rng(600 + k)
+    _, xy, inf = util.rand_points(orc, k, rng, n)
+    s = util.rand_scalars(rng, n)
+    _msm_case(eng, orc, k, xy, inf, s, cs=(0, 11))
+
+
+# ----------------------------------------------------------------------------- pairings
+def test_pairing_parity(eng, orc):
+    rng = np.random.default_rng(700)
+    n = 40
+    _, pxy, pinf = util.rand_points(orc, 1, rng, n)
+    _, qxy, qinf = util.rand_points(orc, 2, rng, n)
+    pinf[1] = 1
+    qinf[2] = 1
+    pinf[3], qinf[3] = 1, 1
+    ml = eng.miller_loop_batch(pxy, pinf, qxy, qinf)
+    oml = orc.miller_loop(pxy, pinf, qxy, qinf, threads=8)
+    assert eq(ml, oml)                                           # MillerLoopResult limb-exact
+    fe = eng.final_exponentiation_batch(ml)
+    ofe = orc.final_exponentiation(oml, threads=8)
+    assert eq(fe, ofe)
+    assert eq(eng.pairing_batch(pxy, pinf, qxy, qinf), ofe)      # == pairing() (src/pairings.rs:607)
+    assert eq(orc.pairing(pxy, pinf, qxy, qinf, threads=8), ofe)
+    # product mode: multi_miller_loop over prepared terms, identities skipped (src/pairings.rs:554-603)
+    mm = eng.multi_miller_loop(pxy[:9], pinf[:9], qxy[:9], qinf[:9])
+    omm = orc.multi_miller_loop(pxy[:9], pinf[:9], qxy[:9], qinf[:9])
+    assert eq(mm, omm)
+    assert eq(eng.final_exponentiation_batch(mm), orc.final_exponentiation(omm))
+    one = np.zeros(72, np.uint64)
+    one[:6] = orc.R_LIMBS
+    assert eq(eng.multi_miller_loop(pxy[:0], None, qxy[:0], None), one)    # MillerLoopResult::default()
+
+
+def test_gt_generator_kat_on_gpu(eng, orc):
+    kat = json.load(open(os.path.join(GOLD, "kat.json")))
+    exp = np.concatenate([np.array([int(x, 16) for x in g], dtype=np.uint64) for g in kat["pairings.rs::generator"]])
+    gxy, ginf = orc.G1.to_affine(orc.G1.generator())
+    hxy, hinf = orc.G2.to_affine(orc.G2.generator())
+    assert eq(eng.pairing_batch(gxy, None, hxy, None), exp)      # src/pairings.rs:827-832
+
+
+def test_imad_peak_runs(eng):
+    v, ms = eng.imad_peak(500)
+    print("IMAD.WIDE peak: %.3e /s (%.3f ms)" % (v, ms))
+    assert v > 1e12
