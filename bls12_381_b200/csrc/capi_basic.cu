@@ -280,6 +280,7 @@ void b200_ctx_destroy(b200_ctx *ctx) {
   }
   if (ctx->arena) cudaFree(ctx->arena);
   if (ctx->stage) cudaFree(ctx->stage);
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   cudaSetDevice(prev);
   delete ctx;
 }
@@ -303,6 +304,37 @@ int b200_ctx_set_msm_window(b200_ctx *ctx, int c) {
   int prev = ctx->msm_c;
   ctx->msm_c = c;
   return prev;
+}
+
+int b200_ctx_set_timing(b200_ctx *ctx, int on) {
+  if (!ctx) return B200_EINVAL;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  ctx->timing = on != 0;
+  ctx->ev_names.clear();
+  return B200_OK;
+}
+int b200_ctx_get_timing(b200_ctx *ctx, char *names, size_t names_len, float *ms, int max) {
+  CHECK_CTX(ctx);
+  if (max < 0 || (max && !ms)) return B200_EINVAL;
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int nrec = (int)ctx->ev_names.size();
+  size_t off = 0;
+  if (names && names_len) names[0] = 0;
+  for (int r = 0; r < nrec && r < max; r++) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, ctx->ev_pool[2 * r], ctx->ev_pool[2 * r + 1]) != cudaSuccess) t = -1.f;
+    ms[r] = t;
+    if (names) {
+      size_t l = strlen(ctx->ev_names[r]);
+      if (off + l + 2 <= names_len) {
+        memcpy(names + off, ctx->ev_names[r], l);
+        off += l;
+        names[off++] = '\n';
+        names[off] = 0;
+      }
+    }
+  }
+  return nrec;
 }
 
 // ================================================================ field tower

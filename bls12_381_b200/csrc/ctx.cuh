@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "../../include/bls12381_b200.h"
 
@@ -22,6 +23,10 @@ struct b200_ctx {
   // staging arena for the host-pointer entry points
   char *stage = nullptr;
   size_t stage_size = 0, stage_off = 0;
+  // optional per-kernel timing (CUDA events on the ctx stream around every launch)
+  bool timing = false;
+  std::vector<cudaEvent_t> ev_pool;       // 2 per record
+  std::vector<const char *> ev_names;     // one per record
 };
 
 namespace b200 {
@@ -76,9 +81,29 @@ inline void *stage_take(b200_ctx *ctx, size_t bytes) {
   return p;
 }
 
+constexpr size_t MAX_TIMING_RECORDS = 8192;
+// returns the index of the record opened (or -1): records an event BEFORE the launch
+inline int timing_begin(b200_ctx *ctx, const char *name) {
+  if (!ctx->timing || ctx->ev_names.size() >= MAX_TIMING_RECORDS) return -1;
+  size_t r = ctx->ev_names.size();
+  while (ctx->ev_pool.size() < 2 * (r + 1)) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return -1;
+    ctx->ev_pool.push_back(e);
+  }
+  ctx->ev_names.push_back(name);
+  cudaEventRecord(ctx->ev_pool[2 * r], ctx->stream);
+  return (int)r;
+}
+inline void timing_end(b200_ctx *ctx, int r) {
+  if (r >= 0) cudaEventRecord(ctx->ev_pool[2 * r + 1], ctx->stream);
+}
+
 #define B200_LAUNCH(ctx, kernel, grid, block, smem, ...)                                 \
   do {                                                                                   \
+    int tr__ = b200::timing_begin(ctx, #kernel);                                         \
     kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                     \
+    b200::timing_end(ctx, tr__);                                                         \
     (ctx)->launches++;                                                                   \
     cudaError_t e__ = cudaGetLastError();                                                \
     if (e__ != cudaSuccess) return b200::set_err(ctx, e__, "launch " #kernel);           \

@@ -84,6 +84,19 @@ class Engine:
     def set_msm_window(self, c):
         return self.lib.b200_ctx_set_msm_window(self.h, int(c))
 
+    def set_timing(self, on=True):
+        self._ck(self.lib.b200_ctx_set_timing(self.h, int(bool(on))), "set_timing")
+
+    def get_timing(self, max_records=8192):
+        """[(kernel_name, ms), ...] for every launch since set_timing(True)"""
+        names = C.create_string_buffer(64 * max_records)
+        ms = (C.c_float * max_records)()
+        n = self.lib.b200_ctx_get_timing(self.h, names, len(names), ms, max_records)
+        if n < 0:
+            self._ck(n, "get_timing")
+        nm = names.value.decode().split("\n")
+        return [(nm[i], float(ms[i])) for i in range(min(n, max_records)) if i < len(nm) and nm[i]]
+
     def imad_peak(self, iters=2000):
         v, ms = C.c_double(), C.c_double()
         self._ck(self.lib.b200_imad_peak(self.h, iters, C.byref(v), C.byref(ms)), "imad_peak")

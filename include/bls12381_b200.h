@@ -64,6 +64,11 @@ int b200_ctx_device(const b200_ctx *ctx);
 void *b200_ctx_stream(const b200_ctx *ctx);
 /* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
 uint64_t b200_ctx_launch_count(const b200_ctx *ctx);
+/* per-kernel timing: when on, every kernel launch of this ctx is bracketed by CUDA events on the ctx
+ * stream.  get_timing synchronises, writes up to `max` durations (ms) and the kernel names joined by
+ * '\n' into `names`, and returns the number of records since the last set_timing call (>= 0). */
+int b200_ctx_set_timing(b200_ctx *ctx, int on);
+int b200_ctx_get_timing(b200_ctx *ctx, char *names, size_t names_len, float *ms, int max);
 /* MSM tuning: window bits c (0 = automatic from n); returns previous value */
 int b200_ctx_set_msm_window(b200_ctx *ctx, int c);
 
@@ -109,8 +114,9 @@ int b200_final_exponentiation_batch(b200_ctx *ctx, const b200_fp12 *in, size_t n
 /* out[i] = pairing(&p[i], &q[i])  :607-653  — n independent Gt values */
 int b200_pairing_batch(b200_ctx *ctx, const b200_g1_affine *p, const uint8_t *p_inf, const b200_g2_affine *q, const uint8_t *q_inf, size_t n, b200_fp12 *gt_out);
 /* out = multi_miller_loop(&[(p_i, G2Prepared::from(q_i))])  :554-603 — ONE MillerLoopResult for the
- * product; equal as a Gt after final_exponentiation (MillerLoopResult is only defined up to factors
- * killed by the final exponentiation; this entry multiplies per-pair Miller values). */
+ * product.  Computed as the Fp12 product of the per-pair Miller values, which is the same field
+ * element the reference's shared-squaring loop produces (f <- f^2 * prod_t l_t is multiplicative), so
+ * the limbs are bit-identical; identity terms contribute one(), like the reference's skip :566-569. */
 int b200_multi_miller_loop(b200_ctx *ctx, const b200_g1_affine *p, const uint8_t *p_inf, const b200_g2_affine *q, const uint8_t *q_inf, size_t n, b200_fp12 *out);
 
 /* ---- device-pointer variants (inputs already resident in HBM; used by bench.py `value`) ------- */
