@@ -63,10 +63,10 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.index, self.rows, self._halt = index, [], threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                     "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
@@ -75,10 +75,10 @@ class ClockSampler(threading.Thread):
                     self.rows.append(f)
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=6)
         sm = sorted(int(float(r[0])) for r in self.rows if r[0].replace(".", "").isdigit())
         reasons = set()
@@ -340,7 +340,9 @@ def main():
         tot_k = sum(share.values()) or 1.0
         if dom in per_kernel:
             launches_dom = len(per_kernel[dom])
-            avg_ms = sum(per_kernel[dom]) / launches_dom
+            # a step may launch the dominant kernel several times (one per window group): its algorithmic work per
+            # STEP over its summed duration per STEP
+            avg_ms = sum(per_kernel[dom]) / a.steps
             # algorithmic work of that kernel per launch, SURVEY §8d cost sheet (FpM x 300 IMAD32):
             if wl in ("g1_msm", "g2_msm"):
                 c = a.window or 16
@@ -363,7 +365,7 @@ def main():
             roof = {"bound": "int (IMAD.WIDE.U32 pipe; SURVEY 8d: not hbm, not tensor)", "kernel": dom,
                     "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "T IMAD32/s", "frac": achieved / peak,
                     "peak_source": "b200_imad_peak microbenchmark run live on this GPU (%.2f ms, dependent-free IMAD.WIDE.U32)" % peak_ms,
-                    "model": "SURVEY 8d cost sheet x 300 IMAD32 per FpM", "kernel_ms_avg": avg_ms, "kernel_launches": launches_dom,
+                    "model": "SURVEY 8d cost sheet x 300 IMAD32 per FpM", "kernel_ms_per_step": avg_ms, "kernel_launches_per_step": launches_dom / a.steps,
                     "kernel_share_of_step": share[dom] / tot_k, "traffic": None,
                     "hbm": {"achieved_gbs": alg_bytes / (avg_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                             "frac": alg_bytes / (avg_ms * 1e-3) / 1e9 / hbm_peak, "of": "measured"},

@@ -258,7 +258,12 @@ int b200_ctx_create(int device, b200_ctx **out) {
   b200_ctx *c = new (std::nothrow) b200_ctx();
   if (!c) return B200_ENOMEM;
   c->device = device;
-  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  bool ok = cudaSetDevice(device) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; ok && i < b200_ctx::N_SYNC_EVENTS; i++) ok = cudaEventCreateWithFlags(&c->ev_sync[i], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {
     delete c;
     cudaSetDevice(prev);
     return B200_ENODEV;
@@ -278,6 +283,16 @@ void b200_ctx_destroy(b200_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamDestroy(ctx->stream);
   }
+  if (ctx->stream2) {
+    cudaStreamSynchronize(ctx->stream2);
+    cudaStreamDestroy(ctx->stream2);
+  }
+  if (ctx->stream3) {
+    cudaStreamSynchronize(ctx->stream3);
+    cudaStreamDestroy(ctx->stream3);
+  }
+  for (int i = 0; i < b200_ctx::N_SYNC_EVENTS; i++)
+    if (ctx->ev_sync[i]) cudaEventDestroy(ctx->ev_sync[i]);
   if (ctx->arena) cudaFree(ctx->arena);
   if (ctx->stage) cudaFree(ctx->stage);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);

@@ -11,7 +11,8 @@
 //                     holds the whole 96/192 MB point set, so the gathers are L2 hits)
 //   5. k_msm_reduce   sum_b (b+1) * B_b per window: per-thread running sums over a chunk of buckets,
 //                     chunk offset by a short double-and-add, shared-memory tree per block
-//   6. k_msm_combine  sums the per-block partials and runs Horner over the windows
+//   6. k_msm_horner   sums the per-block partials and runs Horner over the windows, group by group from
+//                     the top on a side stream, overlapped with steps 4-5 of the lower windows
 //
 // All additions are the reference's COMPLETE formulas (curve.cuh), so duplicate points, P + (-P),
 // identity inputs and zero scalars need no special cases.  Window sharding (shard, n_shards) restricts
@@ -120,13 +121,59 @@ __global__ void __launch_bounds__(256) k_msm_scatter(msm_plan pl, const uint32_t
   });
 }
 
-// one thread per (local window, bucket)
-template <class F>
-__global__ void __launch_bounds__(128) k_msm_accumulate(int nbuckets, size_t total, const char *points, size_t n,
-                                                      const uint32_t *offsets, const uint32_t *hist,
-                                                      const uint32_t *sorted, char *buckets) {
+// ---- bucket scheduling: order (window,bucket) slots by population, largest first, so the 32 lanes of
+// a warp walk buckets of (nearly) equal length (round-1 ncu: 23/32 active lanes with natural order) and
+// the last, partially filled wave holds only the short buckets.  Counting sort on min(count, 1023).
+constexpr int SIZE_BINS = 1024;
+__global__ void __launch_bounds__(256) k_msm_size_hist(size_t total, const uint32_t *hist, uint32_t *size_hist) {
+  __shared__ uint32_t sh[SIZE_BINS];
+  for (int i = threadIdx.x; i < SIZE_BINS; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (k < total) atomicAdd(&sh[min(hist[k], (uint32_t)SIZE_BINS - 1)], 1u);
+  __syncthreads();
+  for (int i = threadIdx.x; i < SIZE_BINS; i += blockDim.x)
+    if (sh[i]) atomicAdd(&size_hist[i], sh[i]);
+}
+// single block: base[bin] = number of slots with a LARGER bin (descending order)
+__global__ void __launch_bounds__(SIZE_BINS) k_msm_size_scan(const uint32_t *size_hist, uint32_t *size_base) {
+  __shared__ uint32_t part[SIZE_BINS];
+  int r = SIZE_BINS - 1 - threadIdx.x;  // thread 0 owns the largest bin
+  uint32_t v = size_hist[r];
+  part[threadIdx.x] = v;
+  __syncthreads();
+  for (int off = 1; off < SIZE_BINS; off <<= 1) {
+    uint32_t a = threadIdx.x >= (unsigned)off ? part[threadIdx.x - off] : 0;
+    __syncthreads();
+    part[threadIdx.x] += a;
+    __syncthreads();
+  }
+  size_base[r] = part[threadIdx.x] - v;
+}
+// warp-aggregated scatter: lanes that hit the same bin are found with match.any, one atomic per group
+__global__ void __launch_bounds__(256) k_msm_size_scatter(size_t total, const uint32_t *hist, const uint32_t *size_base,
+                                                        uint32_t *size_cursor, uint32_t *order) {
   size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (k >= total) return;
+  uint32_t bin = min(hist[k], (uint32_t)SIZE_BINS - 1);
+  unsigned lane = threadIdx.x & 31u;
+  unsigned peers = __match_any_sync(__activemask(), bin);
+  int leader = __ffs(peers) - 1;
+  uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+  uint32_t base = 0;
+  if ((int)lane == leader) base = atomicAdd(&size_cursor[bin], (uint32_t)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  order[size_base[bin] + base + rank] = (uint32_t)k;
+}
+
+// one thread per (local window, bucket), visited in `order`
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_accumulate(int nbuckets, size_t total, size_t slot0, const char *points,
+                                                      size_t n, const uint32_t *offsets, const uint32_t *hist,
+                                                      const uint32_t *sorted, const uint32_t *order, char *buckets) {
+  size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t0 >= total) return;
+  size_t k = slot0 + order[t0];   // `order` holds slot indices relative to the group's first slot
   constexpr size_t FB = field_traits<F>::bytes, AB = 2 * FB, PB = 3 * FB;
   size_t j = k / nbuckets;
   const uint32_t *idx = sorted + j * n + offsets[k];
@@ -184,35 +231,40 @@ __global__ void __launch_bounds__(BLOCK) k_msm_reduce(int nbuckets, int chunk, c
   if (threadIdx.x == 0) proj_store<F>(partials + PB * ((size_t)j * gridDim.x + blockIdx.x), proj_load<F>(smem));
 }
 
-// one block: thread j (< nloc) sums the partials of local window j; thread 0 then runs Horner over
-// ALL windows (identity for windows of other shards): out = sum_{w in shard} 2^(c w) S_w
+// Horner over the windows, one GROUP of windows per launch, top window first, on the ctx's side stream:
+// while the (one-thread, latency-bound) chain  acc <- 2^(c*gap) * acc + S_w  of the upper windows runs,
+// the bucket kernels of the lower windows keep all SMs busy on the main stream; only the last group's
+// step is exposed.  Lanes j < cnt first sum the per-block partials of local window (j_top - j).
+// `prev_w` = global index of the window processed last (-1: none yet); `final_shift` = doublings*c to apply
+// after the group's lowest window (only for the last group of a shard whose lowest window is not 0).
 template <class F>
-__global__ void __launch_bounds__(MAX_WINDOWS) k_msm_combine(msm_plan pl, int parts_per_window, const char *partials,
-                                                           char *out) {
+__global__ void __launch_bounds__(32) k_msm_horner(msm_plan pl, int j_top, int cnt, int prev_w, int final_shift,
+                                                 int parts_per_window, const char *partials, char *hacc) {
   extern __shared__ char smem[];
   constexpr size_t PB = 3 * field_traits<F>::bytes;
-  int j = threadIdx.x;
-  if (j < pl.nloc) {
+  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    int j = j_top - i;
     proj<F> acc = proj_identity<F>();
-    for (int k = 0; k < parts_per_window; k++) acc = proj_add(acc, proj_load<F>(partials + PB * ((size_t)j * parts_per_window + k)));
-    proj_store<F>(smem + PB * j, acc);
+    for (int k = 0; k < parts_per_window; k++)
+      acc = proj_add(acc, proj_load<F>(partials + PB * ((size_t)j * parts_per_window + k)));
+    proj_store<F>(smem + PB * i, acc);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    proj<F> acc = proj_identity<F>();
-    int jj = pl.nloc - 1;
+    proj<F> acc = prev_w < 0 ? proj_identity<F>() : proj_load<F>(hacc);
 #pragma unroll 1
-    for (int w = pl.nwin - 1; w >= 0; w--) {
-      if (jj >= 0 && pl.win[jj] == w) {
-        acc = proj_add(acc, proj_load<F>(smem + PB * jj));
-        jj--;
-      }
-      if (w > 0) {
+    for (int i = 0; i < cnt; i++) {
+      int w = pl.win[j_top - i];
+      if (prev_w >= 0) {
 #pragma unroll 1
-        for (int k = 0; k < pl.c; k++) acc = proj_double(acc);
+        for (int k = (prev_w - w) * pl.c; k > 0; k--) acc = proj_double(acc);
       }
+      acc = proj_add(acc, proj_load<F>(smem + PB * i));
+      prev_w = w;
     }
-    proj_store<F>(out, acc);
+#pragma unroll 1
+    for (int k = final_shift; k > 0; k--) acc = proj_double(acc);
+    proj_store<F>(hacc, acc);
   }
 }
 
@@ -258,27 +310,80 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
   int chunk = (pl.nbuckets + chunks - 1) / chunks;
   if (chunk < 1) chunk = 1;
   int blocks_per_window = chunks / RB;
-  size_t need = 3 * arena_pad(total * 4) + arena_pad((size_t)pl.nloc * n * 4) + arena_pad(total * PB) +
-                arena_pad((size_t)pl.nloc * blocks_per_window * PB) + 4096;
+  size_t need = 4 * arena_pad(total * 4) + 3 * arena_pad(4 * SIZE_BINS * 4) + arena_pad((size_t)pl.nloc * n * 4) +
+                arena_pad(total * PB) + arena_pad((size_t)pl.nloc * blocks_per_window * PB) + arena_pad(PB) + 4096;
   int rc = arena_reserve(ctx, need);
   if (rc != B200_OK) return rc;
   uint32_t *hist = arena_take<uint32_t>(ctx, total);
   uint32_t *cursor = arena_take<uint32_t>(ctx, total);
   uint32_t *offsets = arena_take<uint32_t>(ctx, total);
+  uint32_t *size_hist = arena_take<uint32_t>(ctx, 4 * SIZE_BINS);   // [parity][hist | cursor]
+  uint32_t *size_base = arena_take<uint32_t>(ctx, 2 * SIZE_BINS);   // [parity]
+  uint32_t *order = arena_take<uint32_t>(ctx, total);
   uint32_t *sorted = arena_take<uint32_t>(ctx, (size_t)pl.nloc * n);
   char *buckets = arena_take<char>(ctx, total * PB);
   char *partials = arena_take<char>(ctx, (size_t)pl.nloc * blocks_per_window * PB);
+  char *hacc = arena_take<char>(ctx, PB);
   // hist and cursor are adjacent: one memset
   B200_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)((char *)offsets - (char *)hist), ctx->stream));
   B200_LAUNCH(ctx, k_msm_count, nblk(n, 256), 256, 0, pl, (const uint32_t *)scalars, (const uint8_t *)inf, n, hist);
   B200_LAUNCH(ctx, k_msm_scan, pl.nloc, 1024, 0, pl.nbuckets, hist, offsets);
   B200_LAUNCH(ctx, k_msm_scatter, nblk(n, 256), 256, 0, pl, (const uint32_t *)scalars, (const uint8_t *)inf, n, offsets,
               cursor, sorted);
-  B200_LAUNCH(ctx, k_msm_accumulate<F>, nblk(total, 128), 128, 0, pl.nbuckets, total, (const char *)points, n, offsets,
-              hist, sorted, buckets);
-  dim3 rgrid(blocks_per_window, pl.nloc);
-  B200_LAUNCH(ctx, (k_msm_reduce<F, RB>), rgrid, RB, RB * PB, pl.nbuckets, chunk, buckets, partials);
-  B200_LAUNCH(ctx, k_msm_combine<F>, 1, MAX_WINDOWS, (size_t)pl.nloc * PB, pl, blocks_per_window, partials, (char *)out);
+  // Window groups, top-down.  A group = consecutive local windows = a contiguous range of slots.
+  // Three streams: accumulate(g) on `stream`; reduce(g) on stream2 (after accumulate(g)); horner(g) on
+  // stream3 (after reduce(g) and horner(g-1)).  reduce/horner are latency-bound, few-thread kernels: they
+  // run under the next group's accumulate; only the last group's reduce + Horner step is exposed.
+  int gsz[16], ng = 0;
+  {
+    int left = pl.nloc;
+    if (left >= 12) {
+      gsz[ng++] = (left * 3) / 8; left -= gsz[ng - 1];     // 16 -> 6
+      gsz[ng++] = (left + 1) / 2; left -= gsz[ng - 1];     //       5
+      gsz[ng++] = (left * 3 + 4) / 5; left -= gsz[ng - 1]; //       3
+      gsz[ng++] = left;                                    //       2
+    } else if (left >= 4) {
+      gsz[ng++] = left - left / 2 - (left >= 6 ? 1 : 0); left -= gsz[ng - 1];
+      if (left >= 3) { gsz[ng++] = left - 1; left = 1; }
+      gsz[ng++] = left;
+    } else {
+      gsz[ng++] = left;
+    }
+  }
+  // order the side streams after whatever is still queued on the main stream (previous calls)
+  B200_CUDA(ctx, cudaEventRecord(ctx->ev_sync[0], ctx->stream));
+  B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_sync[0], 0));
+  B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream3, ctx->ev_sync[0], 0));
+  int j_top = pl.nloc - 1, prev_w = -1;
+  for (int g = 0; g < ng; g++) {
+    int cnt = gsz[g], j_lo = j_top - cnt + 1;
+    size_t s0 = (size_t)j_lo * pl.nbuckets, gtotal = (size_t)cnt * pl.nbuckets;
+    // per-group scheduling scratch: SIZE_BINS-sized arrays are double-buffered by group parity
+    uint32_t *sh = size_hist + (size_t)(g & 1) * 2 * SIZE_BINS, *sc = sh + SIZE_BINS;
+    uint32_t *sb = size_base + (size_t)(g & 1) * SIZE_BINS;
+    B200_CUDA(ctx, cudaMemsetAsync(sh, 0, 2 * SIZE_BINS * sizeof(uint32_t), ctx->stream));
+    B200_LAUNCH(ctx, k_msm_size_hist, nblk(gtotal, 256), 256, 0, gtotal, hist + s0, sh);
+    B200_LAUNCH(ctx, k_msm_size_scan, 1, SIZE_BINS, 0, sh, sb);
+    B200_LAUNCH(ctx, k_msm_size_scatter, nblk(gtotal, 256), 256, 0, gtotal, hist + s0, sb, sc, order + s0);
+    B200_LAUNCH(ctx, k_msm_accumulate<F>, nblk(gtotal, 128), 128, 0, pl.nbuckets, gtotal, s0, (const char *)points, n,
+                offsets, hist, sorted, order + s0, buckets);
+    B200_CUDA(ctx, cudaEventRecord(ctx->ev_sync[1 + 2 * g], ctx->stream));
+    B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_sync[1 + 2 * g], 0));
+    dim3 rgrid(blocks_per_window, cnt);
+    B200_LAUNCH_ON(ctx, ctx->stream2, (k_msm_reduce<F, RB>), rgrid, RB, RB * PB, pl.nbuckets, chunk, buckets + PB * s0,
+                   partials + PB * (size_t)j_lo * blocks_per_window);
+    B200_CUDA(ctx, cudaEventRecord(ctx->ev_sync[2 + 2 * g], ctx->stream2));
+    B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream3, ctx->ev_sync[2 + 2 * g], 0));
+    bool last = g == ng - 1;
+    int final_shift = last ? pl.win[0] * pl.c : 0;
+    B200_LAUNCH_ON(ctx, ctx->stream3, k_msm_horner<F>, 1, 32, (size_t)cnt * PB, pl, j_top, cnt, prev_w, final_shift,
+                   blocks_per_window, partials, hacc);
+    prev_w = pl.win[j_lo];
+    j_top = j_lo - 1;
+  }
+  B200_CUDA(ctx, cudaEventRecord(ctx->ev_sync[b200_ctx::N_SYNC_EVENTS - 1], ctx->stream3));
+  B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_sync[b200_ctx::N_SYNC_EVENTS - 1], 0));
+  B200_CUDA(ctx, cudaMemcpyAsync(out, hacc, PB, cudaMemcpyDeviceToDevice, ctx->stream));
   return B200_OK;
 }
 

@@ -12,6 +12,11 @@
 struct b200_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  // side streams of an MSM: bucket reduction (stream2) and the serial Horner chain (stream3) of one window
+  // group overlap the bucket accumulation of the next group on `stream`
+  cudaStream_t stream2 = nullptr, stream3 = nullptr;
+  static constexpr int N_SYNC_EVENTS = 40;
+  cudaEvent_t ev_sync[N_SYNC_EVENTS] = {};
   std::mutex mu;
   char err[256] = {0};
   uint64_t launches = 0;
@@ -83,8 +88,9 @@ inline void *stage_take(b200_ctx *ctx, size_t bytes) {
 
 constexpr size_t MAX_TIMING_RECORDS = 8192;
 // returns the index of the record opened (or -1): records an event BEFORE the launch
-inline int timing_begin(b200_ctx *ctx, const char *name) {
+inline int timing_begin(b200_ctx *ctx, const char *name, cudaStream_t strm = nullptr) {
   if (!ctx->timing || ctx->ev_names.size() >= MAX_TIMING_RECORDS) return -1;
+  if (strm == nullptr) strm = ctx->stream;
   size_t r = ctx->ev_names.size();
   while (ctx->ev_pool.size() < 2 * (r + 1)) {
     cudaEvent_t e;
@@ -92,11 +98,11 @@ inline int timing_begin(b200_ctx *ctx, const char *name) {
     ctx->ev_pool.push_back(e);
   }
   ctx->ev_names.push_back(name);
-  cudaEventRecord(ctx->ev_pool[2 * r], ctx->stream);
+  cudaEventRecord(ctx->ev_pool[2 * r], strm);
   return (int)r;
 }
-inline void timing_end(b200_ctx *ctx, int r) {
-  if (r >= 0) cudaEventRecord(ctx->ev_pool[2 * r + 1], ctx->stream);
+inline void timing_end(b200_ctx *ctx, int r, cudaStream_t strm = nullptr) {
+  if (r >= 0) cudaEventRecord(ctx->ev_pool[2 * r + 1], strm ? strm : ctx->stream);
 }
 
 #define B200_LAUNCH(ctx, kernel, grid, block, smem, ...)                                 \
@@ -104,6 +110,17 @@ inline void timing_end(b200_ctx *ctx, int r) {
     int tr__ = b200::timing_begin(ctx, #kernel);                                         \
     kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                     \
     b200::timing_end(ctx, tr__);                                                         \
+    (ctx)->launches++;                                                                   \
+    cudaError_t e__ = cudaGetLastError();                                                \
+    if (e__ != cudaSuccess) return b200::set_err(ctx, e__, "launch " #kernel);           \
+  } while (0)
+
+// same, on an explicit stream of the ctx
+#define B200_LAUNCH_ON(ctx, strm, kernel, grid, block, smem, ...)                        \
+  do {                                                                                   \
+    int tr__ = b200::timing_begin(ctx, #kernel, strm);                                   \
+    kernel<<<(grid), (block), (smem), (strm)>>>(__VA_ARGS__);                            \
+    b200::timing_end(ctx, tr__, strm);                                                   \
     (ctx)->launches++;                                                                   \
     cudaError_t e__ = cudaGetLastError();                                                \
     if (e__ != cudaSuccess) return b200::set_err(ctx, e__, "launch " #kernel);           \

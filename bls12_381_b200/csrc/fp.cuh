@@ -173,6 +173,12 @@ B200_DEV fp fp_mul(const fp &a, const fp &b) {
 }
 B200_DEV fp fp_sqr(const fp &a) { return fp_mul(a, a); }
 
+// Called (non-inlined) multiply.  nvcc passes the two 12-word operands and the result in registers
+// (no stack traffic — checked in SASS: CALL.REL.NOINC, 0-byte frame), so a group operation becomes
+// ~a dozen calls into ONE 6 KB body that stays resident in the instruction cache, instead of a
+// 70+ KB fully inlined loop body (ncu round 1: `no_instruction` was the top stall of the MSM kernel).
+static __device__ __noinline__ fp fp_mul_c(fp a, fp b) { return fp_mul(a, b); }
+
 // src/fp.rs:382-393
 B200_DEV fp fp_add(const fp &a, const fp &b) {
   fp r;
