@@ -232,26 +232,16 @@ def main():
     t_gen = time.perf_counter() - t_gen
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    from bls12_381_b200.sharding import ShardedMSM
+    sharded = ShardedMSM(eng, k, dist=dist, stream=stream, mode=a.shard) if wl in ("g1_msm", "g2_msm") else None
 
     def step_device():
         if wl == "g1_mul":
             eng.mul_batch_dev(1, pr, sc, out, n_local)
         elif wl == "pairing":
             eng.pairing_batch_dev(pxy, pinf, qxy, qinf, n_local, out)
-        elif world == 1:
-            eng.msm_dev(k, xy, inf, sc, n_local, out)
-        elif a.shard == "window":
-            eng.msm_dev(k, xy, inf, sc, n_local, out, shard=rank, n_shards=world)
-            with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(parts, out)            # 144/288-byte partial per rank over NVLink
-            eng.sum_dev(k, parts, world, out)
         else:
-            lo = rank * (n_local // world)
-            cnt = n_local // world
-            eng.msm_dev(k, xy[lo:lo + cnt], inf[lo:lo + cnt], sc[lo:lo + cnt], cnt, out)
-            with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(parts, out)
-            eng.sum_dev(k, parts, world, out)
+            sharded.msm(xy, inf, sc, n_local, out, parts)            # bls12_381_b200/sharding.py
 
     def barrier():
         torch.cuda.synchronize()

@@ -1,0 +1,186 @@
+// bls12_381.hpp — C++ host-side mirror of the zkcrypto/bls12_381 public surface for the accelerated path,
+// written above the C ABI (include/bls12381_b200.h).  The reference is a Rust crate and this image has no
+// Rust toolchain, so the host layer a Rust user would get from the `-sys` shim is stated
+// here in C++ with the same names, argument meaning and error behaviour:
+//
+//   reference (Rust)                                        this header
+//   -------------------------------------------------------------------------------------------------
+//   &G1Projective * &Scalar            src/g1.rs:556        G1Projective::mul_batch(engine, pts, scalars)
+//   iter.map(|(p,s)| p*s).sum()        src/g1.rs:573,:161   G1Projective::msm(engine, bases, scalars)
+//   G1Projective::batch_normalize      src/g1.rs:806        G1Projective::batch_normalize(engine, p, q)
+//   pairing(&G1Affine,&G2Affine)->Gt   src/pairings.rs:607  pairing_batch(engine, ps, qs)
+//   multi_miller_loop(&[(&p,&q)])      src/pairings.rs:554  multi_miller_loop(engine, ps, qs)
+//   MillerLoopResult::final_exponentiation :48              MillerLoopResult::final_exponentiation(engine)
+//
+// Value types are byte-compatible with the reference's in-memory values (Montgomery limbs), `Copy`-like
+// PODs; fallible calls throw b200::Error carrying the ABI's code and text instead of Rust's CtOption/panic
+// (batch_normalize keeps the reference's `assert_eq!(p.len(), q.len())`, src/g1.rs:807, as an exception).
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/bls12381_b200.h"
+
+namespace bls12_381 {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string &what) : std::runtime_error(what), code(c) {}
+};
+
+// One engine = one GPU (b200_ctx).  Send + Sync in the reference's sense: calls are serialised inside.
+class Engine {
+ public:
+  explicit Engine(int device = -1) {
+    int rc = b200_ctx_create(device, &ctx_);
+    if (rc != B200_OK) throw Error(rc, std::string("b200_ctx_create: ") + b200_strerror(rc));
+  }
+  ~Engine() { b200_ctx_destroy(ctx_); }
+  Engine(const Engine &) = delete;
+  Engine &operator=(const Engine &) = delete;
+  b200_ctx *raw() const { return ctx_; }
+  void check(int rc, const char *what) const {
+    if (rc != B200_OK) throw Error(rc, std::string(what) + ": " + b200_strerror(rc) + " (" + b200_last_error(ctx_) + ")");
+  }
+
+ private:
+  b200_ctx *ctx_ = nullptr;
+};
+
+struct Scalar {
+  b200_scalar bytes;  // == Scalar::to_bytes(): canonical little-endian, < q   (src/scalar.rs:284)
+};
+
+struct G1Affine {
+  b200_g1_affine xy;
+  uint8_t infinity;  // Choice; identity() is (0, 1, infinity = 1)   (src/g1.rs:187-193)
+};
+struct G2Affine {
+  b200_g2_affine xy;
+  uint8_t infinity;
+};
+
+struct G1Projective {
+  b200_g1_projective v;
+
+  // out[i] = pts[i] * scalars[i]  — limb-exact with G1Projective::multiply (src/g1.rs:754-774)
+  static std::vector<G1Projective> mul_batch(const Engine &e, const std::vector<G1Projective> &pts,
+                                             const std::vector<Scalar> &scalars) {
+    if (pts.size() != scalars.size()) throw Error(B200_EINVAL, "mul_batch: length mismatch");
+    std::vector<G1Projective> out(pts.size());
+    e.check(b200_g1_mul_batch(e.raw(), &pts.data()->v, &scalars.data()->bytes, pts.size(), &out.data()->v), "g1_mul_batch");
+    return out;
+  }
+  // sum_i bases[i] * scalars[i]   (src/g1.rs:573-579 + Sum :161-171)
+  static G1Projective msm(const Engine &e, const std::vector<G1Affine> &bases, const std::vector<Scalar> &scalars) {
+    if (bases.size() != scalars.size()) throw Error(B200_EINVAL, "msm: length mismatch");
+    std::vector<b200_g1_affine> xy(bases.size());
+    std::vector<uint8_t> inf(bases.size());
+    for (size_t i = 0; i < bases.size(); i++) {
+      xy[i] = bases[i].xy;
+      inf[i] = bases[i].infinity;
+    }
+    G1Projective out;
+    e.check(b200_g1_msm(e.raw(), xy.data(), inf.data(), &scalars.data()->bytes, bases.size(), &out.v), "g1_msm");
+    return out;
+  }
+  // G1Projective::batch_normalize(p, q): panics (throws) if p.len() != q.len()   (src/g1.rs:806-839)
+  static void batch_normalize(const Engine &e, const std::vector<G1Projective> &p, std::vector<G1Affine> &q) {
+    if (p.size() != q.size()) throw Error(B200_EINVAL, "batch_normalize: assertion `left == right` failed");
+    std::vector<b200_g1_affine> xy(p.size());
+    std::vector<uint8_t> inf(p.size());
+    e.check(b200_g1_batch_normalize(e.raw(), &p.data()->v, p.size(), xy.data(), inf.data()), "g1_batch_normalize");
+    for (size_t i = 0; i < p.size(); i++) q[i] = G1Affine{xy[i], inf[i]};
+  }
+};
+
+struct G2Projective {
+  b200_g2_projective v;
+  static std::vector<G2Projective> mul_batch(const Engine &e, const std::vector<G2Projective> &pts,
+                                             const std::vector<Scalar> &scalars) {
+    if (pts.size() != scalars.size()) throw Error(B200_EINVAL, "mul_batch: length mismatch");
+    std::vector<G2Projective> out(pts.size());
+    e.check(b200_g2_mul_batch(e.raw(), &pts.data()->v, &scalars.data()->bytes, pts.size(), &out.data()->v), "g2_mul_batch");
+    return out;
+  }
+  static G2Projective msm(const Engine &e, const std::vector<G2Affine> &bases, const std::vector<Scalar> &scalars) {
+    if (bases.size() != scalars.size()) throw Error(B200_EINVAL, "msm: length mismatch");
+    std::vector<b200_g2_affine> xy(bases.size());
+    std::vector<uint8_t> inf(bases.size());
+    for (size_t i = 0; i < bases.size(); i++) {
+      xy[i] = bases[i].xy;
+      inf[i] = bases[i].infinity;
+    }
+    G2Projective out;
+    e.check(b200_g2_msm(e.raw(), xy.data(), inf.data(), &scalars.data()->bytes, bases.size(), &out.v), "g2_msm");
+    return out;
+  }
+  static void batch_normalize(const Engine &e, const std::vector<G2Projective> &p, std::vector<G2Affine> &q) {
+    if (p.size() != q.size()) throw Error(B200_EINVAL, "batch_normalize: assertion `left == right` failed");
+    std::vector<b200_g2_affine> xy(p.size());
+    std::vector<uint8_t> inf(p.size());
+    e.check(b200_g2_batch_normalize(e.raw(), &p.data()->v, p.size(), xy.data(), inf.data()), "g2_batch_normalize");
+    for (size_t i = 0; i < p.size(); i++) q[i] = G2Affine{xy[i], inf[i]};
+  }
+};
+
+struct Gt {
+  b200_fp12 v;  // canonical Fp12 (src/pairings.rs:211)
+};
+
+struct MillerLoopResult {
+  b200_fp12 v;  // src/pairings.rs:26 ; Default = Fp12::one()
+  Gt final_exponentiation(const Engine &e) const {  // src/pairings.rs:48-176
+    Gt out;
+    e.check(b200_final_exponentiation_batch(e.raw(), &v, 1, &out.v), "final_exponentiation");
+    return out;
+  }
+};
+
+namespace detail {
+inline void split(const std::vector<G1Affine> &ps, const std::vector<G2Affine> &qs, std::vector<b200_g1_affine> &pxy,
+                  std::vector<uint8_t> &pinf, std::vector<b200_g2_affine> &qxy, std::vector<uint8_t> &qinf) {
+  if (ps.size() != qs.size()) throw Error(B200_EINVAL, "pairing: length mismatch");
+  pxy.resize(ps.size());
+  pinf.resize(ps.size());
+  qxy.resize(ps.size());
+  qinf.resize(ps.size());
+  for (size_t i = 0; i < ps.size(); i++) {
+    pxy[i] = ps[i].xy;
+    pinf[i] = ps[i].infinity;
+    qxy[i] = qs[i].xy;
+    qinf[i] = qs[i].infinity;
+  }
+}
+}  // namespace detail
+
+// out[i] = pairing(&ps[i], &qs[i])   (src/pairings.rs:607-653; identity on either side -> Gt::identity())
+inline std::vector<Gt> pairing_batch(const Engine &e, const std::vector<G1Affine> &ps, const std::vector<G2Affine> &qs) {
+  std::vector<b200_g1_affine> pxy;
+  std::vector<b200_g2_affine> qxy;
+  std::vector<uint8_t> pinf, qinf;
+  detail::split(ps, qs, pxy, pinf, qxy, qinf);
+  std::vector<Gt> out(ps.size());
+  e.check(b200_pairing_batch(e.raw(), pxy.data(), pinf.data(), qxy.data(), qinf.data(), ps.size(), &out.data()->v),
+          "pairing_batch");
+  return out;
+}
+// multi_miller_loop(&[(&p_i, &G2Prepared::from(q_i))])   (src/pairings.rs:554-603)
+inline MillerLoopResult multi_miller_loop(const Engine &e, const std::vector<G1Affine> &ps, const std::vector<G2Affine> &qs) {
+  std::vector<b200_g1_affine> pxy;
+  std::vector<b200_g2_affine> qxy;
+  std::vector<uint8_t> pinf, qinf;
+  detail::split(ps, qs, pxy, pinf, qxy, qinf);
+  MillerLoopResult out;
+  e.check(b200_multi_miller_loop(e.raw(), pxy.data(), pinf.data(), qxy.data(), qinf.data(), ps.size(), &out.v),
+          "multi_miller_loop");
+  return out;
+}
+
+static_assert(sizeof(G1Projective) == 144 && sizeof(G2Projective) == 288 && sizeof(Gt) == 576 && sizeof(Scalar) == 32,
+              "value types must be layout-compatible with the ABI structs");
+
+}  // namespace bls12_381
