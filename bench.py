@@ -139,6 +139,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--shard", default="window", choices=["window", "points"])
     ap.add_argument("--window", type=int, default=0, help="MSM window bits (0 = auto)")
+    ap.add_argument("--tune", action="append", default=[], help="key=value tuning knob (b200_ctx_set_tuning)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     a = ap.parse_args()
@@ -193,6 +194,9 @@ def main():
     eng = bls12_381_b200.Engine(local_rank)
     if a.window:
         eng.set_msm_window(a.window)
+    for kv in a.tune:
+        key, val = kv.split("=")
+        eng.set_tuning(key, int(val))
     dev = torch.device("cuda", local_rank)
     stream = torch.cuda.ExternalStream(eng.stream, device=dev)
     k = 2 if wl == "g2_msm" else 1
@@ -252,6 +256,18 @@ def main():
     for _ in range(a.warmup):
         step_device()
     barrier()
+    verified = None
+    if world > 1 and sharded is not None:
+        # outside the timed region: the sharded result must be the same group element as the one-GPU MSM
+        full = torch.empty_like(out)
+        eng.msm_dev(k, xy, inf, sc, n_local, full)
+        both = torch.cat([out, full]).contiguous()
+        axy = torch.empty((2, AFFW), dtype=torch.int64, device=dev)
+        ainf = torch.empty(2, dtype=torch.uint8, device=dev)
+        eng.batch_normalize_dev(k, both, 2, axy, ainf)
+        verified = bool(torch.equal(axy[0], axy[1]) and ainf[0] == ainf[1])
+        if not verified:
+            raise SystemExit("bench.py: sharded MSM result differs from the single-GPU result on rank %d" % rank)
     eng.set_timing(True)
     launches0 = eng.launches
     sampler = ClockSampler(local_rank)
@@ -383,7 +399,7 @@ def main():
                            ("by pair/item index, no collective" if wl in ("pairing", "g1_mul") else
                             a.shard + "-sharded, one NCCL all-gather of partial sums")),
                            "l2": "256 MiB buffer written between timed steps (L2 flush)",
-                           "input_generation_s": t_gen, "seed": hex(seed)},
+                           "input_generation_s": t_gen, "seed": hex(seed), "sharded_result_equals_single_gpu": verified},
                 "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line))
     if dist is not None:

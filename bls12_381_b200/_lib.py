@@ -20,6 +20,7 @@ SIGNATURES = {
     "b200_ctx_stream": [_vp],
     "b200_ctx_launch_count": [_vp],
     "b200_ctx_set_msm_window": [_vp, _i],
+    "b200_ctx_set_tuning": [_vp, C.c_char_p, _i],
     "b200_ctx_set_timing": [_vp, _i],
     "b200_ctx_get_timing": [_vp, C.c_char_p, _sz, C.POINTER(C.c_float), _i],
     "b200_tower_op": [_vp, _i, _i, _vp, _vp, _vp, _sz],

@@ -15,7 +15,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libbls12381_b200.so")
 OBJ = os.path.join(HERE, "build")
-UNITS = ["capi_basic.cu", "capi_pairing.cu", "capi_msm.cu"]
+# (source, extra nvcc flags).  The pairing kernels are built once per register budget.
+UNITS = [("capi_basic.cu", []), ("capi_pairing.cu", []), ("capi_msm.cu", []),
+         ("pairing_v4.cu", []), ("pairing_v8.cu", ["-maxrregcount=128"])]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
@@ -31,10 +33,10 @@ def _digest():
     h = hashlib.sha256()
     for root in (CSRC, os.path.join(HERE, "..", "include")):
         for f in sorted(os.listdir(root)):
-            if f.endswith((".cu", ".cuh", ".h")):
+            if f.endswith((".cu", ".cuh", ".h", ".inc")):
                 h.update(f.encode())
                 h.update(open(os.path.join(root, f), "rb").read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update((" ".join(NVCC_FLAGS) + repr(UNITS)).encode())
     return h.hexdigest()
 
 
@@ -46,9 +48,10 @@ def build(force=False, verbose=False):
         return OUT
     nvcc = _nvcc()
 
-    def one(unit):
+    def one(spec):
+        unit, extra = spec
         obj = os.path.join(OBJ, unit.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, unit), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, unit), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         open(obj + ".log", "w").write(r.stdout + r.stderr)      # ptxas -v: registers / spills per kernel
         if r.returncode != 0:

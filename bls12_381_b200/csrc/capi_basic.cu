@@ -321,6 +321,23 @@ int b200_ctx_set_msm_window(b200_ctx *ctx, int c) {
   return prev;
 }
 
+int b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int value) {
+  if (!ctx || !key) return B200_EINVAL;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (!strcmp(key, "msm_window")) {
+    if (value != 0 && (value < 2 || value > 24)) return B200_EINVAL;
+    ctx->msm_c = value;
+  } else if (!strcmp(key, "g2_acc_blocks")) {
+    if (value < 2 || value > 3) return B200_EINVAL;
+    ctx->tune_g2_acc_blocks = value;
+  } else if (!strcmp(key, "pairing_blocks")) {
+    if (value != 4 && value != 8) return B200_EINVAL;
+    ctx->tune_pairing_blocks = value;
+  } else {
+    return B200_EINVAL;
+  }
+  return B200_OK;
+}
 int b200_ctx_set_timing(b200_ctx *ctx, int on) {
   if (!ctx) return B200_EINVAL;
   std::lock_guard<std::mutex> g(ctx->mu);

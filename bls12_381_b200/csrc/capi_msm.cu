@@ -167,8 +167,8 @@ __global__ void __launch_bounds__(256) k_msm_size_scatter(size_t total, const ui
 }
 
 // one thread per (local window, bucket), visited in `order`
-template <class F>
-__global__ void __launch_bounds__(128) k_msm_accumulate(int nbuckets, size_t total, size_t slot0, const char *points,
+template <class F, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_msm_accumulate(int nbuckets, size_t total, size_t slot0, const char *points,
                                                       size_t n, const uint32_t *offsets, const uint32_t *hist,
                                                       const uint32_t *sorted, const uint32_t *order, char *buckets) {
   size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -365,8 +365,13 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
     B200_LAUNCH(ctx, k_msm_size_hist, nblk(gtotal, 256), 256, 0, gtotal, hist + s0, sh);
     B200_LAUNCH(ctx, k_msm_size_scan, 1, SIZE_BINS, 0, sh, sb);
     B200_LAUNCH(ctx, k_msm_size_scatter, nblk(gtotal, 256), 256, 0, gtotal, hist + s0, sb, sc, order + s0);
-    B200_LAUNCH(ctx, k_msm_accumulate<F>, nblk(gtotal, 128), 128, 0, pl.nbuckets, gtotal, s0, (const char *)points, n,
-                offsets, hist, sorted, order + s0, buckets);
+    if (sizeof(F) == sizeof(fp) || ctx->tune_g2_acc_blocks <= 2) {
+      B200_LAUNCH(ctx, (k_msm_accumulate<F, (sizeof(F) == sizeof(fp) ? 3 : 2)>), nblk(gtotal, 128), 128, 0, pl.nbuckets, gtotal,
+                  s0, (const char *)points, n, offsets, hist, sorted, order + s0, buckets);
+    } else {
+      B200_LAUNCH(ctx, (k_msm_accumulate<F, 3>), nblk(gtotal, 128), 128, 0, pl.nbuckets, gtotal, s0, (const char *)points, n,
+                  offsets, hist, sorted, order + s0, buckets);
+    }
     B200_CUDA(ctx, cudaEventRecord(ctx->ev_sync[1 + 2 * g], ctx->stream));
     B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_sync[1 + 2 * g], 0));
     dim3 rgrid(blocks_per_window, cnt);

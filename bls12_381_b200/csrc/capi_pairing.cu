@@ -2,74 +2,31 @@
 // product mode behind multi_miller_loop.  One thread per pair; pairs are independent, so batches shard
 // by pair index with no collective.
 #include "ctx.cuh"
-#include "pairing.cuh"
 
 using namespace b200;
 
+#define DECL_VARIANT(v)                                                                                              \
+  int b200_pair_miller_##v(b200_ctx *, const void *, const void *, const void *, const void *, size_t, void *);        \
+  int b200_pair_final_exp_##v(b200_ctx *, const void *, size_t, void *);                                               \
+  int b200_pair_product_##v(b200_ctx *, const void *, size_t, void *);
+DECL_VARIANT(v4) DECL_VARIANT(v8)
+
 namespace {
 
-constexpr unsigned PAIR_BLOCK = 64;
-
-__global__ void __launch_bounds__(PAIR_BLOCK) k_miller_loop(const char *pxy, const uint8_t *pinf, const char *qxy,
-                                                          const uint8_t *qinf, size_t n, char *out) {
-  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  fp12 f;
-  miller_loop_pair(&f, affine_load<fp>(pxy, pinf, i), affine_load<fp2>(qxy, qinf, i));
-  fp12_store(out + 576 * i, &f);
-}
-__global__ void __launch_bounds__(PAIR_BLOCK) k_final_exp(const char *in, size_t n, char *out) {
-  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  fp12 f;
-  fp12_load(&f, in + 576 * i);
-  final_exponentiation(&f);
-  fp12_store(out + 576 * i, &f);
-}
-// product of n Fp12 values: per-thread strided partial products, then a shared-memory tree
-__global__ void __launch_bounds__(PAIR_BLOCK) k_fp12_product(const char *in, size_t n, char *out) {
-  extern __shared__ char smem[];
-  fp12 acc, t;
-  fp12_set_one(&acc);
-  for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
-    fp12_load(&t, in + 576 * i);
-    fp12_mul(&acc, &acc, &t);
-  }
-  fp12_store(smem + 576 * threadIdx.x, &acc);
-  __syncthreads();
-  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-    if ((int)threadIdx.x < s) {
-      fp12_load(&acc, smem + 576 * threadIdx.x);
-      fp12_load(&t, smem + 576 * (threadIdx.x + s));
-      fp12_mul(&acc, &acc, &t);
-      fp12_store(smem + 576 * threadIdx.x, &acc);
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    fp12_load(&acc, smem);
-    fp12_store(out, &acc);
-  }
-}
-
-inline unsigned nblk(size_t n, unsigned b) { return (unsigned)((n + b - 1) / b); }
-
+// register-budget variants of the pairing kernels (pairing_v*.cu); ctx->tune_pairing_blocks selects one
 int miller_dev(b200_ctx *ctx, const void *p, const void *pi, const void *q, const void *qi, size_t n, void *out) {
-  if (n == 0) return B200_OK;
-  B200_LAUNCH(ctx, k_miller_loop, nblk(n, PAIR_BLOCK), PAIR_BLOCK, 0, (const char *)p, (const uint8_t *)pi,
-              (const char *)q, (const uint8_t *)qi, n, (char *)out);
-  return B200_OK;
+  switch (ctx->tune_pairing_blocks) {
+    case 8: return b200_pair_miller_v8(ctx, p, pi, q, qi, n, out);
+    default: return b200_pair_miller_v4(ctx, p, pi, q, qi, n, out);
+  }
 }
 int final_exp_dev(b200_ctx *ctx, const void *in, size_t n, void *out) {
-  if (n == 0) return B200_OK;
-  B200_LAUNCH(ctx, k_final_exp, nblk(n, PAIR_BLOCK), PAIR_BLOCK, 0, (const char *)in, n, (char *)out);
-  return B200_OK;
+  switch (ctx->tune_pairing_blocks) {
+    case 8: return b200_pair_final_exp_v8(ctx, in, n, out);
+    default: return b200_pair_final_exp_v4(ctx, in, n, out);
+  }
 }
-int product_dev(b200_ctx *ctx, const void *in, size_t n, void *out) {
-  // two levels: up to 148*? blocks would need a second pass; n partial products are tiny, one block is enough
-  B200_LAUNCH(ctx, k_fp12_product, 1, PAIR_BLOCK, 576 * PAIR_BLOCK, (const char *)in, n, (char *)out);
-  return B200_OK;
-}
+int product_dev(b200_ctx *ctx, const void *in, size_t n, void *out) { return b200_pair_product_v4(ctx, in, n, out); }
 int sync(b200_ctx *ctx) {
   B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return B200_OK;

@@ -56,31 +56,28 @@ B200_DEV void fp2_store(void *p, const fp2 &a) {
   fp_store(q + 48, a.c1);
 }
 
-// Non-inlined Fp2 mul/sqr: ONE copy of the 3x(305-IMAD) body per kernel instead of one per call site.
-// Everything at Fp2 level and above (G2, Fp6, Fp12, pairing) goes through these: the operands do not
-// fit in registers next to a G2 point anyway, and the instruction cache (and ptxas) stay sane.
+// Called (non-inlined) Fp2 mul/sqr: ONE copy of the body per kernel instead of one per call site.
+// Operands and result travel BY VALUE in registers (48 words in, 24 out — checked in SASS: no STL/LDL,
+// 0-byte frame), and the three/two Fp products inside are calls into the single fp_mul_c body.
+// Everything at Fp2 level and above (G2, Fp6, Fp12, pairing) goes through these.
 #define B200_NOINL static __device__ __noinline__
-B200_NOINL void fp2_mul_ni(fp2 *r, const fp2 *a, const fp2 *b) { *r = fp2_mul(*a, *b); }
-B200_NOINL void fp2_sqr_ni(fp2 *r, const fp2 *a) { *r = fp2_sqr(*a); }
-B200_NOINL void fp_mul_ni(fp *r, const fp *a, const fp *b) { *r = fp_mul(*a, *b); }
-B200_NOINL void fp_inv_ni(fp *r, const fp *a) { *r = fp_inv(*a); }
-B200_DEV fp2 M2(const fp2 &a, const fp2 &b) {
-  fp2 r;
-  fp2_mul_ni(&r, &a, &b);
-  return r;
+B200_NOINL fp2 fp2_mul_c(fp2 a, fp2 b) {
+  fp t0 = fp_mul_c(a.c0, b.c0);
+  fp t1 = fp_mul_c(a.c1, b.c1);
+  fp s = fp_mul_c(fp_add(a.c0, a.c1), fp_add(b.c0, b.c1));
+  return fp2{fp_sub(t0, t1), fp_sub(fp_sub(s, t0), t1)};
 }
-B200_DEV fp2 S2(const fp2 &a) {
-  fp2 r;
-  fp2_sqr_ni(&r, &a);
-  return r;
+B200_NOINL fp2 fp2_sqr_c(fp2 a) {
+  fp s = fp_add(a.c0, a.c1), d = fp_sub(a.c0, a.c1), t = fp_dbl(a.c0);
+  return fp2{fp_mul_c(s, d), fp_mul_c(t, a.c1)};
 }
+B200_NOINL fp fp_inv_c(fp a) { return fp_inv(a); }
+B200_DEV fp2 M2(const fp2 &a, const fp2 &b) { return fp2_mul_c(a, b); }
+B200_DEV fp2 S2(const fp2 &a) { return fp2_sqr_c(a); }
+B200_DEV void fp_mul_ni(fp *r, const fp *a, const fp *b) { *r = fp_mul_c(*a, *b); }
 B200_DEV fp2 fp2_inv_ni(const fp2 &a) {
-  fp n = fp_add(fp_sqr(a.c0), fp_sqr(a.c1)), t;
-  fp_inv_ni(&t, &n);
-  fp nt = fp_neg(t), r0, r1;
-  fp_mul_ni(&r0, &a.c0, &t);
-  fp_mul_ni(&r1, &a.c1, &nt);
-  return fp2{r0, r1};
+  fp t = fp_inv_c(fp_add(fp_mul_c(a.c0, a.c0), fp_mul_c(a.c1, a.c1)));
+  return fp2{fp_mul_c(a.c0, t), fp_mul_c(a.c1, fp_neg(t))};
 }
 
 // ---- uniform names so the curve templates (curve.cuh) work over Fp (G1) and Fp2 (G2)

@@ -84,6 +84,9 @@ class Engine:
     def set_msm_window(self, c):
         return self.lib.b200_ctx_set_msm_window(self.h, int(c))
 
+    def set_tuning(self, key, value):
+        self._ck(self.lib.b200_ctx_set_tuning(self.h, key.encode(), int(value)), "set_tuning(%s)" % key)
+
     def set_timing(self, on=True):
         self._ck(self.lib.b200_ctx_set_timing(self.h, int(bool(on))), "set_timing")
 
