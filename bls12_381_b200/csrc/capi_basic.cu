@@ -330,6 +330,9 @@ int b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int value) {
   } else if (!strcmp(key, "g2_acc_blocks")) {
     if (value < 2 || value > 3) return B200_EINVAL;
     ctx->tune_g2_acc_blocks = value;
+  } else if (!strcmp(key, "pairing_chunks")) {
+    if (value < 1 || value > 64) return B200_EINVAL;
+    ctx->tune_pairing_chunks = value;
   } else if (!strcmp(key, "pairing_blocks")) {
     if (value != 4 && value != 8) return B200_EINVAL;
     ctx->tune_pairing_blocks = value;

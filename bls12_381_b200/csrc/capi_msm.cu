@@ -19,6 +19,7 @@
 // steps 1-5 to windows w = shard (mod n_shards); step 6 then yields sum_{w in shard} 2^(cw) S_w.
 #include "ctx.cuh"
 #include "curve.cuh"
+#include "curve_warp.cuh"
 
 using namespace b200;
 
@@ -240,32 +241,27 @@ __global__ void __launch_bounds__(BLOCK) k_msm_reduce(int nbuckets, int chunk, c
 template <class F>
 __global__ void __launch_bounds__(32) k_msm_horner(msm_plan pl, int j_top, int cnt, int prev_w, int final_shift,
                                                  int parts_per_window, const char *partials, char *hacc) {
-  extern __shared__ char smem[];
   constexpr size_t PB = 3 * field_traits<F>::bytes;
-  for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-    int j = j_top - i;
-    proj<F> acc = proj_identity<F>();
+  const int lane = threadIdx.x;
+  // ONE warp, lane-parallel group operations (curve_warp.cuh): every lane carries the same accumulator
+  proj<F> acc = prev_w < 0 ? proj_identity<F>() : proj_load<F>(hacc);
+#pragma unroll 1
+  for (int i = 0; i < cnt; i++) {
+    int j = j_top - i, w = pl.win[j];
+    proj<F> sw = proj_identity<F>();
+#pragma unroll 1
     for (int k = 0; k < parts_per_window; k++)
-      acc = proj_add(acc, proj_load<F>(partials + PB * ((size_t)j * parts_per_window + k)));
-    proj_store<F>(smem + PB * i, acc);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    proj<F> acc = prev_w < 0 ? proj_identity<F>() : proj_load<F>(hacc);
+      sw = warp_add(sw, proj_load<F>(partials + PB * ((size_t)j * parts_per_window + k)), lane);
+    if (prev_w >= 0) {
 #pragma unroll 1
-    for (int i = 0; i < cnt; i++) {
-      int w = pl.win[j_top - i];
-      if (prev_w >= 0) {
-#pragma unroll 1
-        for (int k = (prev_w - w) * pl.c; k > 0; k--) acc = proj_double(acc);
-      }
-      acc = proj_add(acc, proj_load<F>(smem + PB * i));
-      prev_w = w;
+      for (int k = (prev_w - w) * pl.c; k > 0; k--) acc = warp_double(acc, lane);
     }
-#pragma unroll 1
-    for (int k = final_shift; k > 0; k--) acc = proj_double(acc);
-    proj_store<F>(hacc, acc);
+    acc = warp_add(acc, sw, lane);
+    prev_w = w;
   }
+#pragma unroll 1
+  for (int k = final_shift; k > 0; k--) acc = warp_double(acc, lane);
+  if (lane == 0) proj_store<F>(hacc, acc);
 }
 
 template <class F>
@@ -381,7 +377,7 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
     B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream3, ctx->ev_sync[2 + 2 * g], 0));
     bool last = g == ng - 1;
     int final_shift = last ? pl.win[0] * pl.c : 0;
-    B200_LAUNCH_ON(ctx, ctx->stream3, k_msm_horner<F>, 1, 32, (size_t)cnt * PB, pl, j_top, cnt, prev_w, final_shift,
+    B200_LAUNCH_ON(ctx, ctx->stream3, k_msm_horner<F>, 1, 32, 0, pl, j_top, cnt, prev_w, final_shift,
                    blocks_per_window, partials, hacc);
     prev_w = pl.win[j_lo];
     j_top = j_lo - 1;

@@ -6,25 +6,58 @@
 using namespace b200;
 
 #define DECL_VARIANT(v)                                                                                              \
-  int b200_pair_miller_##v(b200_ctx *, const void *, const void *, const void *, const void *, size_t, void *);        \
-  int b200_pair_final_exp_##v(b200_ctx *, const void *, size_t, void *);                                               \
+  int b200_pair_miller_##v(b200_ctx *, cudaStream_t, const void *, const void *, const void *, const void *, size_t,   \
+                           void *);                                                                                    \
+  int b200_pair_final_exp_##v(b200_ctx *, cudaStream_t, const void *, size_t, void *);                                 \
   int b200_pair_product_##v(b200_ctx *, const void *, size_t, void *);
 DECL_VARIANT(v4) DECL_VARIANT(v8)
 
 namespace {
 
 // register-budget variants of the pairing kernels (pairing_v*.cu); ctx->tune_pairing_blocks selects one
-int miller_dev(b200_ctx *ctx, const void *p, const void *pi, const void *q, const void *qi, size_t n, void *out) {
-  switch (ctx->tune_pairing_blocks) {
-    case 8: return b200_pair_miller_v8(ctx, p, pi, q, qi, n, out);
-    default: return b200_pair_miller_v4(ctx, p, pi, q, qi, n, out);
-  }
+int miller_on(b200_ctx *ctx, cudaStream_t st, const void *p, const void *pi, const void *q, const void *qi, size_t n,
+              void *out) {
+  return ctx->tune_pairing_blocks == 8 ? b200_pair_miller_v8(ctx, st, p, pi, q, qi, n, out)
+                                       : b200_pair_miller_v4(ctx, st, p, pi, q, qi, n, out);
 }
-int final_exp_dev(b200_ctx *ctx, const void *in, size_t n, void *out) {
-  switch (ctx->tune_pairing_blocks) {
-    case 8: return b200_pair_final_exp_v8(ctx, in, n, out);
-    default: return b200_pair_final_exp_v4(ctx, in, n, out);
+int final_exp_on(b200_ctx *ctx, cudaStream_t st, const void *in, size_t n, void *out) {
+  return ctx->tune_pairing_blocks == 8 ? b200_pair_final_exp_v8(ctx, st, in, n, out)
+                                       : b200_pair_final_exp_v4(ctx, st, in, n, out);
+}
+int miller_dev(b200_ctx *ctx, const void *p, const void *pi, const void *q, const void *qi, size_t n, void *out) {
+  return miller_on(ctx, ctx->stream, p, pi, q, qi, n, out);
+}
+int final_exp_dev(b200_ctx *ctx, const void *in, size_t n, void *out) { return final_exp_on(ctx, ctx->stream, in, n, out); }
+
+// Full pairings of a batch: Miller loop then final exponentiation per CHUNK, chunks alternating between the two
+// streams of the ctx.  Every thread of either kernel runs for milliseconds, so a single launch per kernel pays a
+// whole extra wave for the last, partially filled one (2^16 pairs = 1.73 waves of 148 SMs x 4 x 64 threads);
+// with independent chunks in flight the block scheduler back-fills the tail of one kernel with blocks of another.
+int pairing_dev(b200_ctx *ctx, const void *p, const void *pi, const void *q, const void *qi, size_t n, void *out) {
+  int chunks = ctx->tune_pairing_chunks;
+  if (chunks < 1) chunks = 1;
+  if (n < (size_t)chunks * 4096) chunks = 1;
+  if (chunks == 1) {
+    int rc = miller_dev(ctx, p, pi, q, qi, n, out);
+    return rc != B200_OK ? rc : final_exp_dev(ctx, out, n, out);
   }
+  B200_CUDA(ctx, cudaEventRecord(ctx->ev_sync[0], ctx->stream));
+  B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_sync[0], 0));
+  size_t per = ((n + chunks - 1) / chunks + 63) & ~(size_t)63;
+  for (int c = 0; c < chunks; c++) {
+    size_t lo = (size_t)c * per, cnt = lo >= n ? 0 : (n - lo < per ? n - lo : per);
+    if (cnt == 0) break;
+    cudaStream_t st = (c & 1) ? ctx->stream2 : ctx->stream;
+    const char *cp = (const char *)p + 96 * lo, *cq = (const char *)q + 192 * lo;
+    const uint8_t *cpi = pi ? (const uint8_t *)pi + lo : nullptr, *cqi = qi ? (const uint8_t *)qi + lo : nullptr;
+    char *co = (char *)out + 576 * lo;
+    int rc = miller_on(ctx, st, cp, cpi, cq, cqi, cnt, co);
+    if (rc == B200_OK) rc = final_exp_on(ctx, st, co, cnt, co);
+    if (rc != B200_OK) return rc;
+  }
+  B200_CUDA(ctx, cudaEventRecord(ctx->ev_sync[1], ctx->stream2));
+  B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_sync[1], 0));
+  return B200_OK;
 }
 int product_dev(b200_ctx *ctx, const void *in, size_t n, void *out) { return b200_pair_product_v4(ctx, in, n, out); }
 int sync(b200_ctx *ctx) {
@@ -78,8 +111,7 @@ int b200_pairing_batch_dev(b200_ctx *ctx, const void *p, const void *p_inf, cons
                            void *gt_out) {
   CHECK_CTX(ctx);
   if (n && (!p || !q || !gt_out)) return B200_EINVAL;
-  int rc = miller_dev(ctx, p, p_inf, q, q_inf, n, gt_out);
-  if (rc == B200_OK) rc = final_exp_dev(ctx, gt_out, n, gt_out);
+  int rc = pairing_dev(ctx, p, p_inf, q, q_inf, n, gt_out);
   return rc != B200_OK ? rc : sync(ctx);
 }
 int b200_fp12_product_dev(b200_ctx *ctx, const void *in, size_t n, void *out) {
@@ -123,8 +155,7 @@ int b200_pairing_batch(b200_ctx *ctx, const b200_g1_affine *p, const uint8_t *p_
   host_pairs h(ctx, p, p_inf, q, q_inf, n, 576 * n);
   if (h.rc != B200_OK) return h.rc;
   void *dout = stage_take(ctx, 576 * n);
-  int rc = miller_dev(ctx, h.dp, h.dpi, h.dq, h.dqi, n, dout);
-  if (rc == B200_OK) rc = final_exp_dev(ctx, dout, n, dout);
+  int rc = pairing_dev(ctx, h.dp, h.dpi, h.dq, h.dqi, n, dout);
   if (rc != B200_OK) return rc;
   B200_CUDA(ctx, cudaMemcpyAsync(gt_out, dout, 576 * n, cudaMemcpyDeviceToHost, ctx->stream));
   return sync(ctx);

@@ -22,6 +22,7 @@ struct b200_ctx {
   uint64_t launches = 0;
   int msm_c = 0;
   int tune_pairing_blocks = 4; // resident 64-thread blocks/SM the pairing kernels are compiled for (4: 255 regs, measured best; 8: 128 regs, spills)
+  int tune_pairing_chunks = 4; // independent Miller+final-exp chunks of a pairing batch kept in flight on 2 streams
   int tune_g2_acc_blocks = 2;  // resident blocks/SM the G2 bucket kernel is compiled for (2: 255 regs, 3: 168)
   int sm_count = 148;
   // scratch arena (device memory), bump-allocated per API call

@@ -70,7 +70,8 @@ uint64_t b200_ctx_launch_count(const b200_ctx *ctx);
 int b200_ctx_set_timing(b200_ctx *ctx, int on);
 int b200_ctx_get_timing(b200_ctx *ctx, char *names, size_t names_len, float *ms, int max);
 /* tuning knobs by name: "msm_window" (0 = auto, else 2..24), "g2_acc_blocks" (2|3 resident blocks/SM the G2
- * bucket kernel is compiled for).  Unknown key or bad value -> B200_EINVAL. */
+ * bucket kernel is compiled for), "pairing_blocks" (4|8), "pairing_chunks" (1..64 independent chunks of a
+ * pairing batch in flight).  Unknown key or bad value -> B200_EINVAL. */
 int b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int value);
 /* MSM tuning: window bits c (0 = automatic from n); returns previous value */
 int b200_ctx_set_msm_window(b200_ctx *ctx, int c);
