@@ -355,11 +355,12 @@ def main():
                 nwin = (256 + c - 1) // c
                 nwin_local = len(range(rank, nwin, world)) if (world > 1 and a.shard == "window") else nwin
                 n_eff = n if (world == 1 or a.shard == "window") else n // world
-                fpm = (11 if k == 1 else 33) * n_eff * nwin_local      # one complete mixed add per term per window
+                fpm = (11 if k == 1 else 33) * n_eff * nwin_local      # SURVEY 8d model: one complete mixed add per term per window
+                fpm_exec = (10 if k == 1 else 30) * n_eff * nwin_local  # what the kernel executes: XYZZ madd, 8M+2S
             elif wl == "g1_mul":
-                fpm = 5100.0 * n_local
+                fpm = fpm_exec = 5100.0 * n_local
             else:
-                fpm = 9104.0 * n_local                                   # final exponentiation kernel
+                fpm = fpm_exec = 9104.0 * n_local                        # final exponentiation kernel
             achieved = fpm * IMAD_PER_FPM / (avg_ms * 1e-3)
             hbm_peak = None
             try:
@@ -370,6 +371,7 @@ def main():
                          "pairing": 576 * 2 * n_local}[wl]
             roof = {"bound": "int (IMAD.WIDE.U32 pipe; SURVEY 8d: not hbm, not tensor)", "kernel": dom,
                     "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "T IMAD32/s", "frac": achieved / peak,
+                    "executed_frac": fpm_exec * IMAD_PER_FPM / (avg_ms * 1e-3) / peak,
                     "peak_source": "b200_imad_peak microbenchmark run live on this GPU (%.2f ms, dependent-free IMAD.WIDE.U32)" % peak_ms,
                     "model": "SURVEY 8d cost sheet x 300 IMAD32 per FpM", "kernel_ms_per_step": avg_ms, "kernel_launches_per_step": launches_dom / a.steps,
                     "kernel_share_of_step": share[dom] / tot_k, "traffic": None,

@@ -7,15 +7,17 @@
 //   1. k_msm_count    signed c-bit window digits of every scalar -> per-(window,bucket) histogram
 //   2. k_msm_scan     exclusive scan of the histogram (one block per window)
 //   3. k_msm_scatter  counting-sort scatter: point index (+ sign bit) grouped by bucket
-//   4. k_msm_accumulate  one thread per bucket: complete mixed additions of its points (the 126 MB L2
-//                     holds the whole 96/192 MB point set, so the gathers are L2 hits)
+//   4. k_msm_accumulate  one thread per bucket: XYZZ mixed additions (8M+2S) of its points with explicit
+//                     P+P / P+(-P) / empty-accumulator handling (the 126 MB L2 holds the whole 96/192 MB
+//                     point set, so the gathers are L2 hits); the bucket is stored in the reference's
+//                     projective form
 //   5. k_msm_reduce   sum_b (b+1) * B_b per window: per-thread running sums over a chunk of buckets,
 //                     chunk offset by a short double-and-add, shared-memory tree per block
 //   6. k_msm_horner   sums the per-block partials and runs Horner over the windows, group by group from
 //                     the top on a side stream, overlapped with steps 4-5 of the lower windows
 //
-// All additions are the reference's COMPLETE formulas (curve.cuh), so duplicate points, P + (-P),
-// identity inputs and zero scalars need no special cases.  Window sharding (shard, n_shards) restricts
+// Steps 5-6 use the reference's COMPLETE formulas (curve.cuh); step 4's exceptional cases (duplicate points,
+// P + (-P)) are branched on explicitly; identity inputs and zero digits never reach a bucket.  Window sharding (shard, n_shards) restricts
 // steps 1-5 to windows w = shard (mod n_shards); step 6 then yields sum_{w in shard} 2^(cw) S_w.
 #include "ctx.cuh"
 #include "curve.cuh"
@@ -179,15 +181,15 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(int nbuckets, size
   size_t j = k / nbuckets;
   const uint32_t *idx = sorted + j * n + offsets[k];
   uint32_t cnt = hist[k];
-  proj<F> acc = proj_identity<F>();
+  xyzz<F> acc = xyzz_identity<F>();
   for (uint32_t t = 0; t < cnt; t++) {
     uint32_t e = __ldg(idx + t);
     const char *pp = points + AB * (size_t)(e & 0x7fffffffu);
     F x = field_traits<F>::load_ro(pp), y = field_traits<F>::load_ro(pp + FB);
     if (e >> 31) y = f_neg(y);
-    acc = proj_add_mixed_nz(acc, x, y);
+    acc = xyzz_add_mixed(acc, x, y);
   }
-  proj_store<F>(buckets + PB * k, acc);
+  proj_store<F>(buckets + PB * k, xyzz_to_proj(acc));
 }
 
 // small multiple k * P, k < 2^24, by double-and-add (MSB first)

@@ -158,6 +158,57 @@ B200_DEV proj<F> proj_multiply(const proj<F> &s, const uint32_t by[8]) {
   return acc;
 }
 
+// ---- XYZZ accumulator (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2; identity: ZZ = 0) for the MSM buckets.
+// Not a reference type: the reference only has the complete projective formulas above (11 FpM + ~17 field
+// additions per mixed add).  Inside a bucket only the GROUP ELEMENT matters, so buckets use
+// the cheaper madd-2008-s (8M + 2S, 6 field additions) and fall back to explicit handling of the three
+// exceptional cases the incomplete formula has — accumulator = identity, P + P, P + (-P) — which the parity
+// suite exercises (duplicate points, P and -P with equal scalars, all-equal scalars).
+template <class F>
+struct xyzz {
+  F x, y, zz, zzz;
+};
+template <class F>
+B200_DEV xyzz<F> xyzz_identity() {
+  return xyzz<F>{field_traits<F>::zero(), field_traits<F>::one(), field_traits<F>::zero(), field_traits<F>::zero()};
+}
+// acc + (px, py), (px, py) affine and not the identity
+template <class F>
+B200_DEV xyzz<F> xyzz_add_mixed(const xyzz<F> &a, const F &px, const F &py) {
+  if (f_is_zero(a.zz)) return xyzz<F>{px, py, field_traits<F>::one(), field_traits<F>::one()};
+  F u2 = f_mul(px, a.zz);
+  F s2 = f_mul(py, a.zzz);
+  F p = f_sub(u2, a.x);
+  F r = f_sub(s2, a.y);
+  if (f_is_zero(p)) {
+    if (!f_is_zero(r)) return xyzz_identity<F>();  // P + (-P)
+    // P + P: double the affine point (mdbl-2008-s-1 with Z = 1); y = 0 cannot happen on a prime-order subgroup
+    // but is still the identity if it does
+    if (f_is_zero(py)) return xyzz_identity<F>();
+    F u = f_dbl(py);
+    F v = f_sqr(u);
+    F w = f_mul(u, v);
+    F s = f_mul(px, v);
+    F xx = f_sqr(px);
+    F m = f_add(f_dbl(xx), xx);
+    F x3 = f_sub(f_sqr(m), f_dbl(s));
+    F y3 = f_sub(f_mul(m, f_sub(s, x3)), f_mul(w, py));
+    return xyzz<F>{x3, y3, v, w};
+  }
+  F pp = f_sqr(p);
+  F ppp = f_mul(p, pp);
+  F q = f_mul(a.x, pp);
+  F x3 = f_sub(f_sub(f_sqr(r), ppp), f_dbl(q));
+  F y3 = f_sub(f_mul(r, f_sub(q, x3)), f_mul(a.y, ppp));
+  return xyzz<F>{x3, y3, f_mul(a.zz, pp), f_mul(a.zzz, ppp)};
+}
+// same group element in the reference's homogeneous projective form: (X*ZZZ : Y*ZZ : ZZ*ZZZ)
+template <class F>
+B200_DEV proj<F> xyzz_to_proj(const xyzz<F> &a) {
+  if (f_is_zero(a.zz)) return proj_identity<F>();
+  return proj<F>{f_mul(a.x, a.zzz), f_mul(a.y, a.zz), f_mul(a.zz, a.zzz)};
+}
+
 // ---- memory layouts (include/bls12381_b200.h): affine = x||y, projective = x||y||z, limbs as Fp
 template <class F>
 B200_DEV proj<F> proj_load(const void *p) {
