@@ -33,10 +33,10 @@ __global__ void k_tower_op(int op, const uint64_t *a, const uint64_t *b, uint64_
   } else if constexpr (LEVEL == 2) {
     fp2 x = fp2_load(pa), y = pb ? fp2_load(pb) : fp2_zero(), r;
     switch (op) {
-      case B200_OP_MUL: r = fp2_mul(x, y); break;
+      case B200_OP_MUL: r = M2(x, y); break;  // the called, lazily reduced multiply every G2/pairing kernel uses
       case B200_OP_ADD: r = fp2_add(x, y); break;
       case B200_OP_SUB: r = fp2_sub(x, y); break;
-      case B200_OP_SQUARE: r = fp2_sqr(x); break;
+      case B200_OP_SQUARE: r = S2(x); break;
       case B200_OP_NEG: r = fp2_neg(x); break;
       case B200_OP_INVERT: r = fp2_inv(x); break;
       case B200_OP_MUL_BY_NONRESIDUE: r = fp2_mul_by_nonresidue(x); break;

@@ -179,6 +179,140 @@ B200_DEV fp fp_sqr(const fp &a) { return fp_mul(a, a); }
 // 70+ KB fully inlined loop body (ncu round 1: `no_instruction` was the top stall of the MSM kernel).
 static __device__ __noinline__ fp fp_mul_c(fp a, fp b) { return fp_mul(a, b); }
 
+// ---------------------------------------------------------------------------------------------------
+// Lazy reduction support (used by the Fp2 multiplication): an unreduced 768-bit product, its Montgomery
+// reduction, and plain (non-modular) 384/768-bit add/sub.  Karatsuba Fp2 mul = 3 wide products (3 x 144
+// IMAD) + 2 reductions (2 x 156) = 744 IMAD instead of 3 x 300 = 900.  8p < 2^384 leaves room for the
+// unreduced operand sums; every result that leaves these helpers is canonical again.
+struct fpw {
+  uint32_t v[24];
+};
+
+// chain over acc[0..12) += x[0],x[2],..,x[10] * s, then the carry into acc[12] (when it exists)
+template <bool TOP>
+B200_DEV void fp_cmad_row_c(uint32_t *acc, const uint32_t *x, uint32_t s) {
+  fp_cmad_row(acc, x, s);
+  if (TOP) ptx_addc(acc[12], acc[12], 0u);
+}
+
+// t = a * b as a 24-word integer (no reduction).  Even/odd aligned accumulators as in fp_mul.
+B200_DEV fpw fp_mul_wide(const fp &a, const fp &b) {
+  uint32_t E[24], O[24];  // O[k] sits at word k+1
+#pragma unroll
+  for (int k = 0; k < 24; k++) E[k] = O[k] = 0;
+#pragma unroll
+  for (int i = 0; i < 12; i += 2) {
+    // even row i: a_even*b_i at even offset i (E), a_odd*b_i at odd offset i+1 (O index i)
+    fp_cmad_row_c<true>(E + i, a.v, b.v[i]);
+    fp_cmad_row_c<true>(O + i, a.v + 1, b.v[i]);
+    // odd row i+1: a_even*b_{i+1} at odd offset i+1 (O index i), a_odd*b_{i+1} at even offset i+2 (E)
+    fp_cmad_row_c<true>(O + i, a.v, b.v[i + 1]);
+    if (i + 14 < 24)
+      fp_cmad_row_c<true>(E + i + 2, a.v + 1, b.v[i + 1]);
+    else
+      fp_cmad_row_c<false>(E + i + 2, a.v + 1, b.v[i + 1]);  // top chain: no carry out (a*b < 2^768)
+  }
+  fpw t;
+  t.v[0] = E[0];
+  ptx_add_cc(t.v[1], E[1], O[0]);
+#pragma unroll
+  for (int k = 2; k < 23; k++) ptx_addc_cc(t.v[k], E[k], O[k - 1]);
+  ptx_addc(t.v[23], E[23], O[22]);
+  return t;
+}
+B200_DEV fpw fpw_add(const fpw &a, const fpw &b) {  // caller guarantees no overflow of 768 bits
+  fpw r;
+  ptx_add_cc(r.v[0], a.v[0], b.v[0]);
+#pragma unroll
+  for (int k = 1; k < 23; k++) ptx_addc_cc(r.v[k], a.v[k], b.v[k]);
+  ptx_addc(r.v[23], a.v[23], b.v[23]);
+  return r;
+}
+// a - b ; when the difference is negative, p * 2^384 is added (result in [0, p*2^384))
+B200_DEV fpw fpw_sub_mod(const fpw &a, const fpw &b) {
+  fpw r;
+  uint32_t borrow;
+  ptx_sub_cc(r.v[0], a.v[0], b.v[0]);
+#pragma unroll
+  for (int k = 1; k < 24; k++) ptx_subc_cc(r.v[k], a.v[k], b.v[k]);
+  ptx_subc(borrow, 0u, 0u);
+  ptx_add_cc(r.v[12], r.v[12], fp_modw(0) & borrow);
+#pragma unroll
+  for (int k = 1; k < 11; k++) ptx_addc_cc(r.v[12 + k], r.v[12 + k], fp_modw(k) & borrow);
+  ptx_addc(r.v[23], r.v[23], fp_modw(11) & borrow);
+  return r;
+}
+B200_DEV fpw fpw_sub(const fpw &a, const fpw &b) {  // caller guarantees a >= b
+  fpw r;
+  ptx_sub_cc(r.v[0], a.v[0], b.v[0]);
+#pragma unroll
+  for (int k = 1; k < 23; k++) ptx_subc_cc(r.v[k], a.v[k], b.v[k]);
+  ptx_subc(r.v[23], a.v[23], b.v[23]);
+  return r;
+}
+// plain 384-bit a + b (no reduction; caller guarantees < 2^384, e.g. both < p)
+B200_DEV fp fp_add_nr(const fp &a, const fp &b) {
+  fp r;
+  ptx_add_cc(r.v[0], a.v[0], b.v[0]);
+#pragma unroll
+  for (int k = 1; k < 11; k++) ptx_addc_cc(r.v[k], a.v[k], b.v[k]);
+  ptx_addc(r.v[11], a.v[11], b.v[11]);
+  return r;
+}
+// Montgomery reduction of t < p * 2^384:  (t + m p) / 2^384 mod p, canonical.
+//   REDC(t) = REDC(t_low) + t_high, and REDC(t_low) is the interleaved multiplier run with b = 1:
+//   row 0 contributes a*1, rows 1..11 only reduce and shift (the shift is an add-with-carry chain on the
+//   otherwise idle ALU pipe; the IMAD pipe sees 12 x 12 + 12 = 156 multiplies).
+B200_DEV fp fp_redc_wide(const fpw &t) {
+  uint32_t ev[12], od[12];
+#pragma unroll
+  for (int j = 0; j < 12; j += 2) {
+    ev[j] = t.v[j];
+    ev[j + 1] = 0;
+    od[j] = t.v[j + 1];
+    od[j + 1] = 0;
+  }
+  fp_redc_step(ev, od);
+#pragma unroll
+  for (int i = 1; i < 12; i += 2) {
+    // roles as in fp_mul: A = od (aligned at word 0 after the shift), B = ev (shifted in by two words)
+    ptx_add_cc(od[0], od[0], ev[1]);
+#pragma unroll
+    for (int k = 0; k < 10; k++) ptx_addc_cc(ev[k], ev[k + 2], 0u);
+    ptx_addc_cc(ev[10], 0u, 0u);
+    ev[11] = 0;
+    fp_redc_step(od, ev);
+    if (i + 1 < 12) {
+      ptx_add_cc(ev[0], ev[0], od[1]);
+#pragma unroll
+      for (int k = 0; k < 10; k++) ptx_addc_cc(od[k], od[k + 2], 0u);
+      ptx_addc_cc(od[10], 0u, 0u);
+      od[11] = 0;
+      fp_redc_step(ev, od);
+    }
+  }
+  // q_low = (od >> 32) + ev ; result = q_low + t_high, then one conditional subtraction
+  fp r;
+  ptx_add_cc(r.v[0], ev[0], od[1]);
+#pragma unroll
+  for (int k = 1; k < 11; k++) ptx_addc_cc(r.v[k], ev[k], od[k + 1]);
+  ptx_addc(r.v[11], ev[11], 0u);
+  ptx_add_cc(r.v[0], r.v[0], t.v[12]);
+#pragma unroll
+  for (int k = 1; k < 11; k++) ptx_addc_cc(r.v[k], r.v[k], t.v[12 + k]);
+  ptx_addc(r.v[11], r.v[11], t.v[23]);
+  uint32_t d[12], borrow;
+  ptx_sub_cc(d[0], r.v[0], fp_modw(0));
+#pragma unroll
+  for (int k = 1; k < 12; k++) ptx_subc_cc(d[k], r.v[k], fp_modw(k));
+  ptx_subc(borrow, 0u, 0u);
+#pragma unroll
+  for (int k = 0; k < 12; k++) r.v[k] = borrow ? r.v[k] : d[k];
+  return r;
+}
+static __device__ __noinline__ fpw fp_mul_wide_c(fp a, fp b) { return fp_mul_wide(a, b); }
+static __device__ __noinline__ fp fp_redc_wide_c(fpw t) { return fp_redc_wide(t); }
+
 // src/fp.rs:382-393
 B200_DEV fp fp_add(const fp &a, const fp &b) {
   fp r;

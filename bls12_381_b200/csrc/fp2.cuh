@@ -61,6 +61,16 @@ B200_DEV void fp2_store(void *p, const fp2 &a) {
 // 0-byte frame), and the three/two Fp products inside are calls into the single fp_mul_c body.
 // Everything at Fp2 level and above (G2, Fp6, Fp12, pairing) goes through these.
 #define B200_NOINL static __device__ __noinline__
+// Three implementations of the called Fp2 multiply, chosen per translation unit (all return the same
+// canonical element, bit-identical to src/fp2.rs:205-222; measured on B200, round 1):
+//   default            Karatsuba with LAZY reduction: three unreduced 768-bit products, two Montgomery
+//                      reductions (753 IMAD instead of 915).  Best where the IMAD pipe is saturated
+//                      (G2 MSM bucket kernel: -6 % time).  c0 = a0 b0 - a1 b1 (+ p 2^384 if negative),
+//                      c1 = (a0+a1)(b0+b1) - a0 b0 - a1 b1 (never negative; operand sums < 2p not reduced).
+//   B200_FP2_KCALL     Karatsuba over three calls of fp_mul_c: shortest dependent chains; best for the
+//                      latency-bound pairing kernels (2 warps per SMSP), where the lazy variant is 9 % slower.
+//   B200_FP2_KINLINE   Karatsuba with the three/two Fp products inlined side by side (more ILP for ptxas).
+#if defined(B200_FP2_KCALL)
 B200_NOINL fp2 fp2_mul_c(fp2 a, fp2 b) {
   fp t0 = fp_mul_c(a.c0, b.c0);
   fp t1 = fp_mul_c(a.c1, b.c1);
@@ -71,6 +81,23 @@ B200_NOINL fp2 fp2_sqr_c(fp2 a) {
   fp s = fp_add(a.c0, a.c1), d = fp_sub(a.c0, a.c1), t = fp_dbl(a.c0);
   return fp2{fp_mul_c(s, d), fp_mul_c(t, a.c1)};
 }
+#elif defined(B200_FP2_KINLINE)
+B200_NOINL fp2 fp2_mul_c(fp2 a, fp2 b) { return fp2_mul(a, b); }
+B200_NOINL fp2 fp2_sqr_c(fp2 a) { return fp2_sqr(a); }
+#else
+B200_NOINL fp2 fp2_mul_c(fp2 a, fp2 b) {
+  fpw w0 = fp_mul_wide(a.c0, b.c0);
+  fpw w1 = fp_mul_wide(a.c1, b.c1);
+  fpw w2 = fp_mul_wide(fp_add_nr(a.c0, a.c1), fp_add_nr(b.c0, b.c1));
+  fp c1 = fp_redc_wide(fpw_sub(w2, fpw_add(w0, w1)));
+  fp c0 = fp_redc_wide(fpw_sub_mod(w0, w1));
+  return fp2{c0, c1};
+}
+B200_NOINL fp2 fp2_sqr_c(fp2 a) {
+  fp s = fp_add(a.c0, a.c1), d = fp_sub(a.c0, a.c1), t = fp_dbl(a.c0);
+  return fp2{fp_mul_c(s, d), fp_mul_c(t, a.c1)};
+}
+#endif
 B200_NOINL fp fp_inv_c(fp a) { return fp_inv(a); }
 B200_DEV fp2 M2(const fp2 &a, const fp2 &b) { return fp2_mul_c(a, b); }
 B200_DEV fp2 S2(const fp2 &a) { return fp2_sqr_c(a); }

@@ -1,4 +1,5 @@
-// pairing kernels compiled for 4 resident 64-thread blocks per SM
+// pairing kernels, Fp2 multiply = Karatsuba over three fp_mul_c calls (measured best for these kernels)
 #define B200_PAIR_VARIANT v4
 #define B200_PAIR_MINB 4
+#define B200_FP2_KCALL 1
 #include "pairing_kernels.inc"
