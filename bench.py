@@ -39,7 +39,7 @@ IMAD_PER_FPM = 300
 MODEL_FPM = {"g1_mul": 5100.0, "g1_msm": 200.0, "g2_msm": 600.0, "pairing": 16020.0}
 UNIT = {"g1_mul": "G1 scalar-muls/s", "g1_msm": "G1 MSM point-scalar-muls/s", "g2_msm": "G2 MSM point-scalar-muls/s",
         "pairing": "pairings/s"}
-DOMINANT = {"g1_mul": "k_mul_batch", "g1_msm": "k_msm_accumulate", "g2_msm": "k_msm_accumulate",
+DOMINANT = {"g1_mul": "k_mul_batch_warp", "g1_msm": "k_msm_accumulate", "g2_msm": "k_msm_accumulate",
             "pairing": "k_final_exp"}
 
 
@@ -47,6 +47,12 @@ def rand_scalars(seed, n):
     """n canonical 32-byte LE scalars: 64 random bytes reduced mod q (mirrors Scalar::random ->
     from_bytes_wide, src/scalar.rs:646-650, :300-331)."""
     rng = np.random.default_rng(seed)
+    if n > (1 << 21):
+        # very large batches (config 5): 254 uniform random bits (< q), vectorised — statistically equivalent for
+        # the bucket distribution; the exact from_bytes_wide reduction below is a Python big-int loop
+        out = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+        out[:, 31] &= 0x3f
+        return out
     raw = rng.bytes(64 * n)
     out = bytearray(32 * n)
     for i in range(n):

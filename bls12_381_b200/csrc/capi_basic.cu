@@ -5,6 +5,7 @@
 
 #include "ctx.cuh"
 #include "curve.cuh"
+#include "curve_warp.cuh"
 #include "pairing.cuh"
 
 using namespace b200;
@@ -109,6 +110,30 @@ __global__ void __launch_bounds__(128) k_mul_batch(const char *p, const uint32_t
   proj_store<F>(out + PB * i, proj_multiply(proj_load<F>(p + PB * i), by));
 }
 
+// Small batches (config 1 has 1024 items = 8 warps' worth of threads on 148 SMs): one WARP per item with the
+// lane-parallel group operations of curve_warp.cuh — 3 dependent multiplication levels per doubling and 2 per
+// addition instead of 8 + 12 sequential ones.  Same formulas and values as multiply(); the addition is
+// skipped (not computed-and-discarded) when the scalar bit is 0 — the GPU path is variable-time by design.
+template <class F>
+__global__ void __launch_bounds__(128) k_mul_batch_warp(const char *p, const uint32_t *s, char *out, size_t n) {
+  size_t item = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (item >= n) return;
+  constexpr size_t PB = 3 * field_traits<F>::bytes;
+  uint32_t by[8];
+  const uint4 *sp = reinterpret_cast<const uint4 *>(s + 8 * item);
+  uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
+  by[0] = lo.x; by[1] = lo.y; by[2] = lo.z; by[3] = lo.w;
+  by[4] = hi.x; by[5] = hi.y; by[6] = hi.z; by[7] = hi.w;
+  proj<F> base = proj_load<F>(p + PB * item), acc = proj_identity<F>();
+#pragma unroll 1
+  for (int bit = 254; bit >= 0; bit--) {
+    acc = warp_double(acc, lane);
+    if ((by[bit >> 5] >> (bit & 31)) & 1) acc = warp_add(acc, base, lane);
+  }
+  if (lane == 0) proj_store<F>(out + PB * item, acc);
+}
+
 // batch_normalize (src/g1.rs:806-839): Montgomery's trick per thread over a strided subsequence
 // i = t, t+T, t+2T, ... (coalesced across the warp).  One inversion per thread.  The prefix products
 // are parked in out.x exactly like the reference parks them in q.x.
@@ -181,6 +206,10 @@ inline unsigned nblk(size_t n, unsigned b) { return (unsigned)((n + b - 1) / b);
 template <class F>
 int mul_batch_dev(b200_ctx *ctx, const void *p, const void *s, size_t n, void *out) {
   if (n == 0) return B200_OK;
+  if (n <= 6000) {  // latency regime: one warp per item (crossover with the thread-per-item kernel ~ 4-5 waves)
+    B200_LAUNCH(ctx, k_mul_batch_warp<F>, nblk(n * 32, 128), 128, 0, (const char *)p, (const uint32_t *)s, (char *)out, n);
+    return B200_OK;
+  }
   // small batches: 32-thread blocks so the work spreads over more SMs
   unsigned block = n <= 32u * 1024u ? 32u : 128u;
   B200_LAUNCH(ctx, k_mul_batch<F>, nblk(n, block), block, 0, (const char *)p, (const uint32_t *)s, (char *)out, n);

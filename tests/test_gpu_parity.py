@@ -105,7 +105,7 @@ def test_group_ops(eng, orc, k):
     assert eq(gx, np.concatenate([ox] * 30)) and eq(gi, np.concatenate([oi] * 30))
 
 
-@pytest.mark.parametrize("k,n", [(1, 1024), (2, 192)])
+@pytest.mark.parametrize("k,n", [(1, 1024), (2, 192), (1, 6500)])
 def test_mul_batch_config1(eng, orc, k, n):
     """BASELINE config 1: 1024 x G1Projective * Scalar, raw (x,y,z) limb-exact vs multiply() (src/g1.rs:754)."""
     rng = np.random.default_rng(400 + k)
