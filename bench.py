@@ -380,7 +380,11 @@ def main():
                     "executed_frac": fpm_exec * IMAD_PER_FPM / (avg_ms * 1e-3) / peak,
                     "peak_source": "b200_imad_peak microbenchmark run live on this GPU (%.2f ms, dependent-free IMAD.WIDE.U32)" % peak_ms,
                     "model": "SURVEY 8d cost sheet x 300 IMAD32 per FpM", "kernel_ms_per_step": avg_ms, "kernel_launches_per_step": launches_dom / a.steps,
-                    "kernel_share_of_step": share[dom] / tot_k, "traffic": None,
+                    "kernel_share_of_step": share[dom] / tot_k,
+                    # dram__bytes_read+write of this kernel per step from the ncu --set full capture under profiles/
+                    # (497 MB for the 6-window launch of the 2^20 G1 MSM, scaled to the 16 windows of a step)
+                    "traffic": (497.3e6 * 16 / 6 if (wl == "g1_msm" and log2n == 20 and world == 1) else None),
+                    "traffic_source": "profiles/r01_ncu_full_k_msm_accumulate_g1_final.txt",
                     "hbm": {"achieved_gbs": alg_bytes / (avg_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                             "frac": alg_bytes / (avg_ms * 1e-3) / 1e9 / hbm_peak, "of": "measured"},
                     "kernel_ms": {kname: sum(v) / a.steps for kname, v in per_kernel.items()}}
