@@ -47,6 +47,8 @@ for _g in ("g1", "g2"):
         "b200_%s_msm_dev" % _g: [_vp, _vp, _vp, _vp, _sz, _vp],
         "b200_%s_msm_shard_dev" % _g: [_vp, _vp, _vp, _vp, _sz, _i, _i, _vp],
         "b200_%s_sum_dev" % _g: [_vp, _vp, _sz, _vp],
+        "b200_%s_serialize" % _g: [_vp, _vp, _vp, _sz, _i, _vp],
+        "b200_%s_deserialize" % _g: [_vp, _vp, _sz, _i, _vp, _vp, _vp],
     })
 _RESTYPE = {"b200_ctx_destroy": None, "b200_strerror": C.c_char_p, "b200_last_error": C.c_char_p,
             "b200_ctx_stream": _vp, "b200_ctx_launch_count": C.c_uint64}

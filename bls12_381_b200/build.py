@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libbls12381_b200.so")
 OBJ = os.path.join(HERE, "build")
 # (source, extra nvcc flags).  The pairing kernels are built once per register budget.
-UNITS = [("capi_basic.cu", []), ("capi_pairing.cu", []), ("capi_msm.cu", []),
+UNITS = [("capi_basic.cu", []), ("capi_pairing.cu", []), ("capi_msm.cu", []), ("capi_serial.cu", []),
          ("pairing_v4.cu", []), ("pairing_v8.cu", [])]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

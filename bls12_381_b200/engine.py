@@ -161,6 +161,27 @@ class Engine:
         self._ck(getattr(self.lib, self._g(k) + "msm")(self.h, _hp(xy), _hp(inf), _hp(s), xy.shape[0], _hp(out)), "msm")
         return out
 
+    # ---------------------------------------------------------------- (de)serialization
+    def serialize(self, k, xy, inf=None, compressed=True):
+        """G{k}Affine::to_compressed / to_uncompressed for a batch -> (n, 48k | 96k) uint8"""
+        xy = _np(xy, np.uint64, self.AFF[k])
+        inf = None if inf is None else _np(inf, np.uint8)
+        out = np.empty((xy.shape[0], (48 if compressed else 96) * k), np.uint8)
+        self._ck(getattr(self.lib, self._g(k) + "serialize")(self.h, _hp(xy), _hp(inf), xy.shape[0], int(compressed),
+                                                            _hp(out)), "serialize")
+        return out
+
+    def deserialize(self, k, data, compressed=True):
+        """from_{un,}compressed_unchecked + is_on_curve -> (xy, inf, status); status bit0 = Some, bit1 = on curve"""
+        data = _np(data, np.uint8, (48 if compressed else 96) * k)
+        n = data.shape[0]
+        xy = np.empty((n, self.AFF[k]), np.uint64)
+        inf = np.empty(n, np.uint8)
+        st = np.empty(n, np.uint8)
+        self._ck(getattr(self.lib, self._g(k) + "deserialize")(self.h, _hp(data), n, int(compressed), _hp(xy), _hp(inf),
+                                                              _hp(st)), "deserialize")
+        return xy, inf, st
+
     # ---------------------------------------------------------------- pairings, host pointers
     def _pairs(self, pxy, pinf, qxy, qinf):
         pxy, qxy = _np(pxy, np.uint64, 12), _np(qxy, np.uint64, 24)

@@ -123,6 +123,19 @@ int b200_pairing_batch(b200_ctx *ctx, const b200_g1_affine *p, const uint8_t *p_
  * the limbs are bit-identical; identity terms contribute one(), like the reference's skip :566-569. */
 int b200_multi_miller_loop(b200_ctx *ctx, const b200_g1_affine *p, const uint8_t *p_inf, const b200_g2_affine *q, const uint8_t *q_inf, size_t n, b200_fp12 *out);
 
+/* ---- point (de)serialization on the device (wire format src/notes/serialization.rs) -----
+ * serialize: out[i] = G1Affine::to_compressed (48 B) / to_uncompressed (96 B)  src/g1.rs:221-260
+ *            (G2: 96 / 192 B, Fp2 as c1 || c0                                   src/g2.rs:254-299)
+ * deserialize: G1Affine::from_compressed_unchecked / from_uncompressed_unchecked (src/g1.rs:275-390,
+ *            src/g2.rs:313-464).  status[i] bit 0 = the reference constructor would return Some (canonical
+ *            field encodings, consistent flags, x on the curve for compressed input); bit 1 = is_on_curve
+ *            (src/g1.rs:414).  Rejected inputs yield the identity.  The subgroup test is_torsion_free is NOT
+ *            performed by these entry points. */
+int b200_g1_serialize(b200_ctx *ctx, const b200_g1_affine *p, const uint8_t *inf, size_t n, int compressed, uint8_t *out);
+int b200_g2_serialize(b200_ctx *ctx, const b200_g2_affine *p, const uint8_t *inf, size_t n, int compressed, uint8_t *out);
+int b200_g1_deserialize(b200_ctx *ctx, const uint8_t *in, size_t n, int compressed, b200_g1_affine *out, uint8_t *out_inf, uint8_t *status);
+int b200_g2_deserialize(b200_ctx *ctx, const uint8_t *in, size_t n, int compressed, b200_g2_affine *out, uint8_t *out_inf, uint8_t *status);
+
 /* ---- device-pointer variants (inputs already resident in HBM; used by bench.py `value`) ------- */
 int b200_g1_mul_batch_dev(b200_ctx *ctx, const void *p, const void *s, size_t n, void *out);
 int b200_g2_mul_batch_dev(b200_ctx *ctx, const void *p, const void *s, size_t n, void *out);

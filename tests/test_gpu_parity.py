@@ -220,3 +220,59 @@ def test_imad_peak_runs(eng):
     v, ms = eng.imad_peak(500)
     print("IMAD.WIDE peak: %.3e /s (%.3f ms)" % (v, ms))
     assert v > 1e12
+
+
+# ----------------------------------------------------------------------------- (de)serialization (SURVEY §8f rows 1-2)
+@pytest.mark.parametrize("k", [1, 2])
+def test_serialization_golden_files(eng, orc, k):
+    """[i]G, i < 1000, serialized ON THE GPU must reproduce the reference's .dat golden files byte for byte
+    (src/tests/mod.rs:3-76), and the goldens must deserialize on the GPU to the same points."""
+    dat = np.load(os.path.join(GOLD, "dat_vectors.npz"))
+    unc = dat["g%d_uncompressed" % k].reshape(1000, 96 * k)
+    cmp_ = dat["g%d_compressed" % k].reshape(1000, 48 * k)
+    G = orc.G1 if k == 1 else orc.G2
+    # [i]G on the GPU: prefix sums by repeated mixed addition would be serial; use i as the scalar instead
+    s = np.zeros((1000, 32), np.uint8)
+    s[:, 0] = np.arange(1000) & 0xff
+    s[:, 1] = np.arange(1000) >> 8
+    xy, inf = eng.batch_normalize(k, eng.mul_batch(k, np.repeat(G.generator(), 1000, 0), s))
+    assert inf[0] == 1 and not inf[1:].any()
+    assert np.array_equal(eng.serialize(k, xy, inf, compressed=False), unc)
+    assert np.array_equal(eng.serialize(k, xy, inf, compressed=True), cmp_)
+    for compressed, data in ((False, unc), (True, cmp_)):
+        dxy, dinf, st = eng.deserialize(k, data, compressed=compressed)
+        assert (st == 3).all() and eq(dinf, inf) and eq(dxy, xy)
+
+
+@pytest.mark.parametrize("k", [1, 2])
+def test_deserialization_rejects(eng, orc, k):
+    G = orc.G1 if k == 1 else orc.G2
+    rng = np.random.default_rng(900 + k)
+    _, xy, inf = util.rand_points(orc, k, rng, 8)
+    unc = eng.serialize(k, xy, inf, compressed=False)
+    cmp_ = eng.serialize(k, xy, inf, compressed=True)
+    for i in range(8):
+        assert np.array_equal(unc[i], G.to_uncompressed(xy[i], inf[i])) and np.array_equal(cmp_[i], G.to_compressed(xy[i], inf[i]))
+    bad_u, bad_c = unc.copy(), cmp_.copy()
+    bad_u[0, 0] |= 0x80                          # compression flag on an uncompressed encoding
+    bad_u[1, 0] |= 0x20                          # sort flag on an uncompressed encoding
+    bad_u[2, :48 * k] = 0xff                     # non-canonical x (>= p)
+    bad_u[2, 0] = 0x1f
+    bad_u[3, -1] ^= 1                            # y off the curve: Some, but not on the curve
+    bad_u[4, 0] |= 0x40                          # infinity flag with non-zero coordinates
+    bad_c[0, 0] &= 0x7f                          # compression flag missing
+    bad_c[1, :] = 0
+    bad_c[1, 0] = 0xc0                           # the identity, valid
+    bad_c[2, :] = 0
+    bad_c[2, 0] = 0xe0                           # identity with the sort flag: invalid
+    _, _, st_u = eng.deserialize(k, bad_u, compressed=False)
+    dxy, dinf, st_c = eng.deserialize(k, bad_c, compressed=True)
+    for i in range(8):
+        ok, p, pinf = G.from_uncompressed(bad_u[i])          # oracle: unchecked + on-curve in one flag
+        assert bool(st_u[i] == 3) == ok, ("uncompressed", i, st_u[i])
+        ok, p, pinf = G.from_compressed(bad_c[i])
+        assert bool(st_c[i] & 1) == ok, ("compressed", i, st_c[i])
+        if ok:
+            assert dinf[i] == pinf and (pinf or eq(dxy[i], p))
+    assert st_u[3] == 1 and st_u[0] == 0 and st_u[1] == 0 and st_u[2] == 0 and st_u[4] == 0
+    assert st_c[0] == 0 and st_c[1] == 3 and dinf[1] == 1 and st_c[2] == 0
