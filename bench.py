@@ -346,6 +346,8 @@ def main():
         per_kernel = {}
         for name, ms in timing:
             base = name.split("<")[0].strip("( ")
+            if base.startswith("k_msm_accumulate"):
+                base = "k_msm_accumulate"           # G1 / G2-register / G2-shared-memory variants of the bucket kernel
             per_kernel.setdefault(base, []).append(ms)
         dom = DOMINANT[wl]
         share = {kname: sum(v) for kname, v in per_kernel.items()}

@@ -192,6 +192,93 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(int nbuckets, size
   proj_store<F>(buckets + PB * k, xyzz_to_proj(acc));
 }
 
+// ---- G2 variant of the bucket kernel: the XYZZ accumulator (4 x Fp2 = 96 words) lives in SHARED memory,
+// word-interleaved across the 128 threads of the block (word w of thread t at sm[w*128 + t]: conflict-free),
+// and the madd is ordered so that at most ~4 Fp2 values are live at once.  With the accumulator in registers
+// the kernel needs 255 registers (2 blocks/SM, ~48 % of the IMAD pipe); this form is built for 3 blocks/SM.
+struct sm_fp2 {
+  uint32_t *p;  // &sm[component * 24 * 128 + tid]
+  B200_DEV fp2 get() const {
+    fp2 r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.c0.v[i] = p[i * 128];
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.c1.v[i] = p[(12 + i) * 128];
+    return r;
+  }
+  B200_DEV void set(const fp2 &a) const {
+#pragma unroll
+    for (int i = 0; i < 12; i++) p[i * 128] = a.c0.v[i];
+#pragma unroll
+    for (int i = 0; i < 12; i++) p[(12 + i) * 128] = a.c1.v[i];
+  }
+};
+// rare path (same x): kept out of line so it does not inflate the hot loop's register allocation
+static __device__ __noinline__ void g2sm_same_x(uint32_t *smt, const char *pt, bool negate, bool r_is_zero, bool *empty) {
+  const sm_fp2 X{smt}, Y{smt + 24 * 128}, ZZ{smt + 48 * 128}, ZZZ{smt + 72 * 128};
+  fp2 px = fp2_load_ro(pt), py = fp2_load_ro(pt + 96);
+  if (negate) py = fp2_neg(py);
+  if (!r_is_zero || fp2_is_zero(py)) {  // P + (-P)
+    *empty = true;
+    return;
+  }
+  xyzz<fp2> d = xyzz_add_mixed(xyzz<fp2>{X.get(), Y.get(), ZZ.get(), ZZZ.get()}, px, py);  // takes its P + P branch
+  X.set(d.x);
+  Y.set(d.y);
+  ZZ.set(d.zz);
+  ZZZ.set(d.zzz);
+}
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_msm_accumulate_g2sm(int nbuckets, size_t total, size_t slot0, const char *points,
+                                                                 size_t n, const uint32_t *offsets, const uint32_t *hist,
+                                                                 const uint32_t *sorted, const uint32_t *order, char *buckets) {
+  extern __shared__ uint32_t sm[];
+  size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t0 >= total) return;
+  size_t k = slot0 + order[t0];
+  size_t j = k / nbuckets;
+  const uint32_t *idx = sorted + j * n + offsets[k];
+  uint32_t cnt = hist[k];
+  const sm_fp2 X{sm + threadIdx.x}, Y{sm + 24 * 128 + threadIdx.x}, ZZ{sm + 48 * 128 + threadIdx.x},
+      ZZZ{sm + 72 * 128 + threadIdx.x};
+  bool empty = true;
+  for (uint32_t t = 0; t < cnt; t++) {
+    uint32_t e = __ldg(idx + t);
+    const char *pp_ = points + 192 * (size_t)(e & 0x7fffffffu);
+    fp2 px = fp2_load_ro(pp_), py = fp2_load_ro(pp_ + 96);
+    if (e >> 31) py = fp2_neg(py);
+    if (empty) {
+      X.set(px);
+      Y.set(py);
+      ZZ.set(fp2_one());
+      ZZZ.set(fp2_one());
+      empty = false;
+      continue;
+    }
+    fp2 p = fp2_sub(M2(px, ZZ.get()), X.get());
+    fp2 r = fp2_sub(M2(py, ZZZ.get()), Y.get());
+    if (fp2_is_zero(p)) {  // same x: P + P or P + (-P)   (rare; see xyzz_add_mixed)
+      g2sm_same_x(sm + threadIdx.x, pp_, (e >> 31) != 0, fp2_is_zero(r), &empty);
+      continue;
+    }
+    fp2 pp = S2(p);
+    ZZ.set(M2(ZZ.get(), pp));
+    fp2 ppp = M2(p, pp);
+    ZZZ.set(M2(ZZZ.get(), ppp));
+    fp2 q = M2(X.get(), pp);
+    fp2 x3 = fp2_sub(fp2_sub(S2(r), ppp), fp2_dbl(q));
+    fp2 tt = M2(Y.get(), ppp);
+    X.set(x3);
+    Y.set(fp2_sub(M2(r, fp2_sub(q, x3)), tt));
+  }
+  proj<fp2> out = proj_identity<fp2>();
+  if (!empty) {
+    fp2 zz = ZZ.get(), zzz = ZZZ.get();
+    out = proj<fp2>{M2(X.get(), zzz), M2(Y.get(), zz), M2(zz, zzz)};
+  }
+  proj_store<fp2>(buckets + (size_t)288 * k, out);
+}
+
 // small multiple k * P, k < 2^24, by double-and-add (MSB first)
 template <class F>
 __device__ proj<F> proj_mul_small(const proj<F> &p, uint32_t k) {
@@ -363,12 +450,18 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
     B200_LAUNCH(ctx, k_msm_size_hist, nblk(gtotal, 256), 256, 0, gtotal, hist + s0, sh);
     B200_LAUNCH(ctx, k_msm_size_scan, 1, SIZE_BINS, 0, sh, sb);
     B200_LAUNCH(ctx, k_msm_size_scatter, nblk(gtotal, 256), 256, 0, gtotal, hist + s0, sb, sc, order + s0);
-    if (sizeof(F) == sizeof(fp) || ctx->tune_g2_acc_blocks <= 2) {
-      B200_LAUNCH(ctx, (k_msm_accumulate<F, (sizeof(F) == sizeof(fp) ? 3 : 2)>), nblk(gtotal, 128), 128, 0, pl.nbuckets, gtotal,
-                  s0, (const char *)points, n, offsets, hist, sorted, order + s0, buckets);
-    } else {
+    if (sizeof(F) == sizeof(fp)) {
       B200_LAUNCH(ctx, (k_msm_accumulate<F, 3>), nblk(gtotal, 128), 128, 0, pl.nbuckets, gtotal, s0, (const char *)points, n,
                   offsets, hist, sorted, order + s0, buckets);
+    } else if (ctx->tune_g2_acc_blocks == 2) {   // accumulator in registers: 255 regs, 2 blocks/SM
+      B200_LAUNCH(ctx, (k_msm_accumulate<F, 2>), nblk(gtotal, 128), 128, 0, pl.nbuckets, gtotal, s0, (const char *)points, n,
+                  offsets, hist, sorted, order + s0, buckets);
+    } else if (ctx->tune_g2_acc_blocks == 3) {   // accumulator in shared memory, built for 3 blocks/SM
+      B200_LAUNCH(ctx, (k_msm_accumulate_g2sm<3>), nblk(gtotal, 128), 128, 96 * 128 * 4, pl.nbuckets, gtotal, s0,
+                  (const char *)points, n, offsets, hist, sorted, order + s0, buckets);
+    } else {                                     // accumulator in shared memory, 2 blocks/SM (255 regs)
+      B200_LAUNCH(ctx, (k_msm_accumulate_g2sm<2>), nblk(gtotal, 128), 128, 96 * 128 * 4, pl.nbuckets, gtotal, s0,
+                  (const char *)points, n, offsets, hist, sorted, order + s0, buckets);
     }
     B200_CUDA(ctx, cudaEventRecord(ctx->ev_sync[1 + 2 * g], ctx->stream));
     B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_sync[1 + 2 * g], 0));

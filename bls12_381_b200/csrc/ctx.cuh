@@ -23,7 +23,9 @@ struct b200_ctx {
   int msm_c = 0;
   int tune_pairing_blocks = 4; // resident 64-thread blocks/SM the pairing kernels are compiled for (4: 255 regs, measured best; 8: 128 regs, spills)
   int tune_pairing_chunks = 4; // independent Miller+final-exp chunks of a pairing batch kept in flight on 2 streams
-  int tune_g2_acc_blocks = 2;  // resident blocks/SM the G2 bucket kernel is compiled for (2: 255 regs, 3: 168)
+  // G2 bucket kernel: 2 = accumulator in registers (255 regs, 2 blocks/SM); 3 = accumulator in shared memory, built
+  // for 3 blocks/SM (168 regs); 4 = shared-memory accumulator, 2 blocks/SM (measured best: 31.2 vs 33.1 ms at 2^20)
+  int tune_g2_acc_blocks = 4;
   int sm_count = 148;
   // scratch arena (device memory), bump-allocated per API call
   char *arena = nullptr;

@@ -276,3 +276,25 @@ def test_deserialization_rejects(eng, orc, k):
             assert dinf[i] == pinf and (pinf or eq(dxy[i], p))
     assert st_u[3] == 1 and st_u[0] == 0 and st_u[1] == 0 and st_u[2] == 0 and st_u[4] == 0
     assert st_c[0] == 0 and st_c[1] == 3 and dinf[1] == 1 and st_c[2] == 0
+
+
+@pytest.mark.parametrize("mode", [2, 3, 4])
+def test_g2_msm_bucket_kernel_variants(eng, orc, mode):
+    """the three G2 bucket kernels (accumulator in registers / in shared memory, 3 or 2 blocks per SM) agree with
+    the oracle, including the same-x exceptional cases"""
+    rng = np.random.default_rng(1000)
+    k = 2
+    _, xy, inf = util.rand_points(orc, k, rng, 200)
+    s = util.rand_scalars(rng, 200)
+    xy[5] = xy[4]
+    s[5] = s[4]                                    # P + P inside a bucket
+    xy[7] = xy[6]
+    xy[7, 12:] = orc.tower(2, "neg", xy[6, 12:])
+    s[7] = s[6]                                    # P + (-P) inside a bucket
+    s[8:40] = s[8]                                 # one crowded bucket per window
+    inf[9] = 1
+    eng.set_tuning("g2_acc_blocks", mode)
+    try:
+        _msm_case(eng, orc, k, xy, inf, s, cs=(0, 6, 12))
+    finally:
+        eng.set_tuning("g2_acc_blocks", 4)
