@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) k_msm_size_scatter(size_t total, const ui
 }
 
 // one thread per (local window, bucket), visited in `order`
-template <class F, int MINB>
+template <class F, int MINB, bool PREFETCH>
 __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(int nbuckets, size_t total, size_t slot0, const char *points,
                                                       size_t n, const uint32_t *offsets, const uint32_t *hist,
                                                       const uint32_t *sorted, const uint32_t *order, char *buckets) {
@@ -182,12 +182,54 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(int nbuckets, size
   const uint32_t *idx = sorted + j * n + offsets[k];
   uint32_t cnt = hist[k];
   xyzz<F> acc = xyzz_identity<F>();
-  for (uint32_t t = 0; t < cnt; t++) {
-    uint32_t e = __ldg(idx + t);
-    const char *pp = points + AB * (size_t)(e & 0x7fffffffu);
-    F x = field_traits<F>::load_ro(pp), y = field_traits<F>::load_ro(pp + FB);
-    if (e >> 31) y = f_neg(y);
-    acc = xyzz_add_mixed(acc, x, y);
+  if constexpr (PREFETCH) {
+    // software pipeline: the NEXT point of the bucket is copied global -> shared with cp.async (LDGSTS, no
+    // registers held across the ~3000-instruction addition) while the current addition runs.  Double buffer,
+    // 16-byte chunks interleaved across the block's threads (conflict-free LDS.128).
+    extern __shared__ uint4 pf[];
+    constexpr int NCH = (int)(AB / 16);
+    auto issue = [&](int buf, uint32_t e) {
+      const char *src = points + AB * (size_t)(e & 0x7fffffffu);
+#pragma unroll
+      for (int c = 0; c < NCH; c++) {
+        unsigned dst = (unsigned)__cvta_generic_to_shared(&pf[(buf * NCH + c) * 128 + threadIdx.x]);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + 16 * c) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    uint32_t e = cnt ? __ldg(idx) : 0u;
+    if (cnt) issue(0, e);
+    for (uint32_t t = 0; t < cnt; t++) {
+      uint32_t e_next = 0;
+      if (t + 1 < cnt) {
+        e_next = __ldg(idx + t + 1);
+        issue((t + 1) & 1, e_next);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      const uint4 *b = &pf[((t & 1) * NCH) * 128 + threadIdx.x];
+      uint32_t w[AB / 4];
+#pragma unroll
+      for (int c = 0; c < NCH; c++) {
+        uint4 v = b[c * 128];
+        w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+      }
+      F x, y;
+      memcpy(&x, w, FB);
+      memcpy(&y, w + FB / 4, FB);
+      if (e >> 31) y = f_neg(y);
+      acc = xyzz_add_mixed(acc, x, y);
+      e = e_next;
+    }
+  } else {
+    for (uint32_t t = 0; t < cnt; t++) {
+      uint32_t e = __ldg(idx + t);
+      const char *pp = points + AB * (size_t)(e & 0x7fffffffu);
+      F x = field_traits<F>::load_ro(pp), y = field_traits<F>::load_ro(pp + FB);
+      if (e >> 31) y = f_neg(y);
+      acc = xyzz_add_mixed(acc, x, y);
+    }
   }
   proj_store<F>(buckets + PB * k, xyzz_to_proj(acc));
 }
@@ -411,10 +453,6 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
   char *hacc = arena_take<char>(ctx, PB);
   // hist and cursor are adjacent: one memset
   B200_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)((char *)offsets - (char *)hist), ctx->stream));
-  B200_LAUNCH(ctx, k_msm_count, nblk(n, 256), 256, 0, pl, (const uint32_t *)scalars, (const uint8_t *)inf, n, hist);
-  B200_LAUNCH(ctx, k_msm_scan, pl.nloc, 1024, 0, pl.nbuckets, hist, offsets);
-  B200_LAUNCH(ctx, k_msm_scatter, nblk(n, 256), 256, 0, pl, (const uint32_t *)scalars, (const uint8_t *)inf, n, offsets,
-              cursor, sorted);
   // Window groups, top-down.  A group = consecutive local windows = a contiguous range of slots.
   // Three streams: accumulate(g) on `stream`; reduce(g) on stream2 (after accumulate(g)); horner(g) on
   // stream3 (after reduce(g) and horner(g-1)).  reduce/horner are latency-bound, few-thread kernels: they
@@ -439,10 +477,28 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
   B200_CUDA(ctx, cudaEventRecord(ctx->ev_sync[0], ctx->stream));
   B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_sync[0], 0));
   B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream3, ctx->ev_sync[0], 0));
+  // counting sort of (window, bucket) -> point-index lists, per group: group 0 on the main stream, group g+1 on
+  // stream2 while accumulate(g) runs
+  auto sort_group = [&](cudaStream_t st, int j_lo, int cnt) -> int {
+    msm_plan pg = pl;
+    pg.nloc = cnt;
+    for (int i = 0; i < cnt; i++) pg.win[i] = pl.win[j_lo + i];
+    size_t s0 = (size_t)j_lo * pl.nbuckets;
+    B200_LAUNCH_ON(ctx, st, k_msm_count, nblk(n, 256), 256, 0, pg, (const uint32_t *)scalars, (const uint8_t *)inf, n, hist + s0);
+    B200_LAUNCH_ON(ctx, st, k_msm_scan, cnt, 1024, 0, pl.nbuckets, hist + s0, offsets + s0);
+    B200_LAUNCH_ON(ctx, st, k_msm_scatter, nblk(n, 256), 256, 0, pg, (const uint32_t *)scalars, (const uint8_t *)inf, n,
+                   offsets + s0, cursor + s0, sorted + (size_t)j_lo * n);
+    return B200_OK;
+  };
+  {
+    int rc0 = sort_group(ctx->stream, pl.nloc - gsz[0], gsz[0]);
+    if (rc0 != B200_OK) return rc0;
+  }
   int j_top = pl.nloc - 1, prev_w = -1;
   for (int g = 0; g < ng; g++) {
     int cnt = gsz[g], j_lo = j_top - cnt + 1;
     size_t s0 = (size_t)j_lo * pl.nbuckets, gtotal = (size_t)cnt * pl.nbuckets;
+    if (g > 0) B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_sync[20 + g], 0));  // sort(g) done on stream2
     // per-group scheduling scratch: SIZE_BINS-sized arrays are double-buffered by group parity
     uint32_t *sh = size_hist + (size_t)(g & 1) * 2 * SIZE_BINS, *sc = sh + SIZE_BINS;
     uint32_t *sb = size_base + (size_t)(g & 1) * SIZE_BINS;
@@ -450,11 +506,16 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
     B200_LAUNCH(ctx, k_msm_size_hist, nblk(gtotal, 256), 256, 0, gtotal, hist + s0, sh);
     B200_LAUNCH(ctx, k_msm_size_scan, 1, SIZE_BINS, 0, sh, sb);
     B200_LAUNCH(ctx, k_msm_size_scatter, nblk(gtotal, 256), 256, 0, gtotal, hist + s0, sb, sc, order + s0);
-    if (sizeof(F) == sizeof(fp)) {
-      B200_LAUNCH(ctx, (k_msm_accumulate<F, 3>), nblk(gtotal, 128), 128, 0, pl.nbuckets, gtotal, s0, (const char *)points, n,
+    if constexpr (sizeof(F) == sizeof(fp)) {
+      if (ctx->tune_g1_prefetch) {
+      B200_LAUNCH(ctx, (k_msm_accumulate<F, 3, true>), nblk(gtotal, 128), 128, 2 * 2 * field_traits<F>::bytes * 128, pl.nbuckets,
+                  gtotal, s0, (const char *)points, n, offsets, hist, sorted, order + s0, buckets);
+      } else {
+      B200_LAUNCH(ctx, (k_msm_accumulate<F, 3, false>), nblk(gtotal, 128), 128, 0, pl.nbuckets, gtotal, s0, (const char *)points, n,
                   offsets, hist, sorted, order + s0, buckets);
+      }
     } else if (ctx->tune_g2_acc_blocks == 2) {   // accumulator in registers: 255 regs, 2 blocks/SM
-      B200_LAUNCH(ctx, (k_msm_accumulate<F, 2>), nblk(gtotal, 128), 128, 0, pl.nbuckets, gtotal, s0, (const char *)points, n,
+      B200_LAUNCH(ctx, (k_msm_accumulate<F, 2, false>), nblk(gtotal, 128), 128, 0, pl.nbuckets, gtotal, s0, (const char *)points, n,
                   offsets, hist, sorted, order + s0, buckets);
     } else if (ctx->tune_g2_acc_blocks == 3) {   // accumulator in shared memory, built for 3 blocks/SM
       B200_LAUNCH(ctx, (k_msm_accumulate_g2sm<3>), nblk(gtotal, 128), 128, 96 * 128 * 4, pl.nbuckets, gtotal, s0,
@@ -464,6 +525,11 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
                   (const char *)points, n, offsets, hist, sorted, order + s0, buckets);
     }
     B200_CUDA(ctx, cudaEventRecord(ctx->ev_sync[1 + 2 * g], ctx->stream));
+    if (g + 1 < ng) {  // sort the next group under this group's accumulate
+      int rc1 = sort_group(ctx->stream2, j_lo - gsz[g + 1], gsz[g + 1]);
+      if (rc1 != B200_OK) return rc1;
+      B200_CUDA(ctx, cudaEventRecord(ctx->ev_sync[20 + g + 1], ctx->stream2));
+    }
     B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_sync[1 + 2 * g], 0));
     dim3 rgrid(blocks_per_window, cnt);
     B200_LAUNCH_ON(ctx, ctx->stream2, (k_msm_reduce<F, RB>), rgrid, RB, RB * PB, pl.nbuckets, chunk, buckets + PB * s0,

@@ -22,6 +22,7 @@ struct b200_ctx {
   uint64_t launches = 0;
   int msm_c = 0;
   int tune_pairing_blocks = 4; // resident 64-thread blocks/SM the pairing kernels are compiled for (4: 255 regs, measured best; 8: 128 regs, spills)
+  int tune_g1_prefetch = 1;    // G1 bucket kernel: cp.async double-buffered prefetch of the next point (1) or plain loads (0)
   int tune_pairing_chunks = 4; // independent Miller+final-exp chunks of a pairing batch kept in flight on 2 streams
   // G2 bucket kernel: 2 = accumulator in registers (255 regs, 2 blocks/SM); 3 = accumulator in shared memory, built
   // for 3 blocks/SM (168 regs); 4 = shared-memory accumulator, 2 blocks/SM (measured best: 31.2 vs 33.1 ms at 2^20)
