@@ -24,6 +24,7 @@ SIGNATURES = {
     "b200_ctx_set_timing": [_vp, _i],
     "b200_ctx_get_timing": [_vp, C.c_char_p, _sz, C.POINTER(C.c_float), _i],
     "b200_tower_op": [_vp, _i, _i, _vp, _vp, _vp, _sz],
+    "b200_glv_decompose": [_vp, _vp, _sz, _vp, _vp],
     "b200_imad_peak": [_vp, _i, C.POINTER(C.c_double), C.POINTER(C.c_double)],
     "b200_miller_loop_batch": [_vp, _vp, _vp, _vp, _vp, _sz, _vp],
     "b200_final_exponentiation_batch": [_vp, _vp, _sz, _vp],

@@ -359,6 +359,9 @@ int b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int value) {
   } else if (!strcmp(key, "g2_acc_blocks")) {
     if (value < 2 || value > 4) return B200_EINVAL;  // 2: registers; 3: shared memory, 3 blocks/SM; 4: shared, 2 blocks
     ctx->tune_g2_acc_blocks = value;
+  } else if (!strcmp(key, "g1_glv")) {
+    if (value < 0 || value > 2) return B200_EINVAL;
+    ctx->tune_g1_glv = value;
   } else if (!strcmp(key, "g1_prefetch")) {
     ctx->tune_g1_prefetch = value != 0;
   } else if (!strcmp(key, "pairing_chunks")) {

@@ -22,6 +22,7 @@
 #include "ctx.cuh"
 #include "curve.cuh"
 #include "curve_warp.cuh"
+#include "glv.cuh"
 
 using namespace b200;
 
@@ -34,8 +35,11 @@ struct msm_plan {
   int nwin;       // total windows = ceil(256 / c)
   int nloc;       // windows handled by this shard
   int nbuckets;   // 2^(c-1) per window
+  int glv;        // G1 only: scalars are split k = k1 + k2*lambda, entries refer to P (half 0) or phi(P) (half 1)
   int win[MAX_WINDOWS];  // global index of local window j
 };
+// entry of a bucket's point list: bits 0..29 point index, bit 30 = phi(P) instead of P (GLV), bit 31 = negate
+constexpr uint32_t ENT_NEG = 0x80000000u, ENT_PHI = 0x40000000u, ENT_IDX = 0x3fffffffu;
 
 // signed digit of window w for a canonical 256-bit little-endian scalar held in 8 words.
 // digits d_w in [-2^(c-1), 2^(c-1)], sum_w d_w 2^(cw) == s.  Returns magnitude and sign.
@@ -55,23 +59,35 @@ __device__ __forceinline__ void load_scalar(uint32_t s[8], const uint32_t *scala
   s[4] = hi.x; s[5] = hi.y; s[6] = hi.z; s[7] = hi.w;
 }
 
-// Walks the windows of scalar i; calls f(local_window_index, bucket (0-based magnitude-1), negative)
-// for every non-zero digit whose window belongs to this shard.
+// Walks the windows of one scalar; calls f(local_window_index, bucket (0-based magnitude-1), flags) for every
+// non-zero signed digit whose window belongs to this shard.  flags = ENT_NEG and/or ENT_PHI.
 template <class Fn>
-__device__ __forceinline__ void for_each_digit(const msm_plan &pl, const uint32_t s[8], Fn f) {
+__device__ __forceinline__ void walk_digits(const msm_plan &pl, const uint32_t v[8], uint32_t base_flags, Fn f) {
   uint32_t carry = 0;
   int j = 0;
   const uint32_t half = 1u << (pl.c - 1);
   for (int w = 0; w < pl.nwin; w++) {
-    uint32_t d = window_bits(s, w * pl.c, pl.c) + carry;
+    uint32_t d = window_bits(v, w * pl.c, pl.c) + carry;
     bool neg = d > half;
     carry = neg ? 1u : 0u;
     uint32_t mag = neg ? (1u << pl.c) - d : d;
     if (j < pl.nloc && pl.win[j] == w) {
-      if (mag != 0) f(j, mag - 1u, neg);
+      if (mag != 0) f(j, mag - 1u, base_flags ^ (neg ? ENT_NEG : 0u));
       j++;
     }
   }
+}
+template <class Fn>
+__device__ __forceinline__ void for_each_digit(const msm_plan &pl, const uint32_t s[8], Fn f) {
+  if (!pl.glv) {
+    walk_digits(pl, s, 0u, f);
+    return;
+  }
+  glv_parts g = glv_decompose(s);
+  uint32_t v[8] = {g.k1[0], g.k1[1], g.k1[2], g.k1[3], 0u, 0u, 0u, 0u};
+  walk_digits(pl, v, g.neg1 ? ENT_NEG : 0u, f);
+  v[0] = g.k2[0]; v[1] = g.k2[1]; v[2] = g.k2[2]; v[3] = g.k2[3];
+  walk_digits(pl, v, ENT_PHI | (g.neg2 ? ENT_NEG : 0u), f);
 }
 
 __global__ void __launch_bounds__(256) k_msm_count(msm_plan pl, const uint32_t *scalars, const uint8_t *inf, size_t n,
@@ -81,7 +97,7 @@ __global__ void __launch_bounds__(256) k_msm_count(msm_plan pl, const uint32_t *
   if (inf && inf[i]) return;
   uint32_t s[8];
   load_scalar(s, scalars, i);
-  for_each_digit(pl, s, [&](int j, uint32_t b, bool) { atomicAdd(&hist[(size_t)j * pl.nbuckets + b], 1u); });
+  for_each_digit(pl, s, [&](int j, uint32_t b, uint32_t) { atomicAdd(&hist[(size_t)j * pl.nbuckets + b], 1u); });
 }
 
 // one block per local window: offsets[b] = exclusive prefix of hist over buckets; cursor := 0
@@ -111,16 +127,17 @@ __global__ void __launch_bounds__(1024) k_msm_scan(int nbuckets, const uint32_t 
 }
 
 __global__ void __launch_bounds__(256) k_msm_scatter(msm_plan pl, const uint32_t *scalars, const uint8_t *inf, size_t n,
-                                                   const uint32_t *offsets, uint32_t *cursor, uint32_t *sorted) {
+                                                   size_t sstride, const uint32_t *offsets, uint32_t *cursor,
+                                                   uint32_t *sorted) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (inf && inf[i]) return;
   uint32_t s[8];
   load_scalar(s, scalars, i);
-  for_each_digit(pl, s, [&](int j, uint32_t b, bool neg) {
+  for_each_digit(pl, s, [&](int j, uint32_t b, uint32_t flags) {
     size_t k = (size_t)j * pl.nbuckets + b;
     uint32_t pos = offsets[k] + atomicAdd(&cursor[k], 1u);
-    sorted[(size_t)j * n + pos] = (uint32_t)i | (neg ? 0x80000000u : 0u);
+    sorted[(size_t)j * sstride + pos] = (uint32_t)i | flags;
   });
 }
 
@@ -172,14 +189,15 @@ __global__ void __launch_bounds__(256) k_msm_size_scatter(size_t total, const ui
 // one thread per (local window, bucket), visited in `order`
 template <class F, int MINB, bool PREFETCH>
 __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(int nbuckets, size_t total, size_t slot0, const char *points,
-                                                      size_t n, const uint32_t *offsets, const uint32_t *hist,
-                                                      const uint32_t *sorted, const uint32_t *order, char *buckets) {
+                                                      const char *bx, size_t sstride, const uint32_t *offsets,
+                                                      const uint32_t *hist, const uint32_t *sorted,
+                                                      const uint32_t *order, char *buckets) {
   size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (t0 >= total) return;
   size_t k = slot0 + order[t0];   // `order` holds slot indices relative to the group's first slot
   constexpr size_t FB = field_traits<F>::bytes, AB = 2 * FB, PB = 3 * FB;
   size_t j = k / nbuckets;
-  const uint32_t *idx = sorted + j * n + offsets[k];
+  const uint32_t *idx = sorted + j * sstride + offsets[k];
   uint32_t cnt = hist[k];
   xyzz<F> acc = xyzz_identity<F>();
   if constexpr (PREFETCH) {
@@ -189,11 +207,14 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(int nbuckets, size
     extern __shared__ uint4 pf[];
     constexpr int NCH = (int)(AB / 16);
     auto issue = [&](int buf, uint32_t e) {
-      const char *src = points + AB * (size_t)(e & 0x7fffffffu);
+      const char *src = points + AB * (size_t)(e & ENT_IDX);
+      // GLV: phi(P) = (beta x, y): x comes from the precomputed beta*x array, y from the point
+      const char *srcx = (e & ENT_PHI) ? bx + FB * (size_t)(e & ENT_IDX) : src;
 #pragma unroll
       for (int c = 0; c < NCH; c++) {
         unsigned dst = (unsigned)__cvta_generic_to_shared(&pf[(buf * NCH + c) * 128 + threadIdx.x]);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + 16 * c) : "memory");
+        const char *g = c < NCH / 2 ? srcx + 16 * c : src + 16 * c;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g) : "memory");
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -225,8 +246,8 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(int nbuckets, size
   } else {
     for (uint32_t t = 0; t < cnt; t++) {
       uint32_t e = __ldg(idx + t);
-      const char *pp = points + AB * (size_t)(e & 0x7fffffffu);
-      F x = field_traits<F>::load_ro(pp), y = field_traits<F>::load_ro(pp + FB);
+      const char *pp = points + AB * (size_t)(e & ENT_IDX);
+      F x = field_traits<F>::load_ro((e & ENT_PHI) ? bx + FB * (size_t)(e & ENT_IDX) : pp), y = field_traits<F>::load_ro(pp + FB);
       if (e >> 31) y = f_neg(y);
       acc = xyzz_add_mixed(acc, x, y);
     }
@@ -272,21 +293,21 @@ static __device__ __noinline__ void g2sm_same_x(uint32_t *smt, const char *pt, b
 }
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_msm_accumulate_g2sm(int nbuckets, size_t total, size_t slot0, const char *points,
-                                                                 size_t n, const uint32_t *offsets, const uint32_t *hist,
+                                                                 size_t sstride, const uint32_t *offsets, const uint32_t *hist,
                                                                  const uint32_t *sorted, const uint32_t *order, char *buckets) {
   extern __shared__ uint32_t sm[];
   size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (t0 >= total) return;
   size_t k = slot0 + order[t0];
   size_t j = k / nbuckets;
-  const uint32_t *idx = sorted + j * n + offsets[k];
+  const uint32_t *idx = sorted + j * sstride + offsets[k];
   uint32_t cnt = hist[k];
   const sm_fp2 X{sm + threadIdx.x}, Y{sm + 24 * 128 + threadIdx.x}, ZZ{sm + 48 * 128 + threadIdx.x},
       ZZZ{sm + 72 * 128 + threadIdx.x};
   bool empty = true;
   for (uint32_t t = 0; t < cnt; t++) {
     uint32_t e = __ldg(idx + t);
-    const char *pp_ = points + 192 * (size_t)(e & 0x7fffffffu);
+    const char *pp_ = points + 192 * (size_t)(e & ENT_IDX);
     fp2 px = fp2_load_ro(pp_), py = fp2_load_ro(pp_ + 96);
     if (e >> 31) py = fp2_neg(py);
     if (empty) {
@@ -319,6 +340,26 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accumulate_g2sm(int nbuckets,
     out = proj<fp2>{M2(X.get(), zzz), M2(Y.get(), zz), M2(zz, zzz)};
   }
   proj_store<fp2>(buckets + (size_t)288 * k, out);
+}
+
+// GLV prologue: bx[i] = beta * x_i  (x-coordinate of phi(P_i))
+__global__ void __launch_bounds__(256) k_msm_glv_bx(const char *points, size_t n, char *bx) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fp_store(bx + 48 * i, fp_mul(fp_load_ro(points + 96 * i), fp_const(K_GLV_BETA)));
+}
+// test surface for the decomposition: out[i] = k1 (16 B LE) | k2 (16 B LE), sign[i] = neg1 | neg2 << 1
+__global__ void k_glv_decompose(const uint32_t *scalars, size_t n, uint32_t *out, uint8_t *sign) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t s[8];
+  load_scalar(s, scalars, i);
+  glv_parts g = glv_decompose(s);
+  for (int k = 0; k < 4; k++) {
+    out[8 * i + k] = g.k1[k];
+    out[8 * i + 4 + k] = g.k2[k];
+  }
+  sign[i] = (g.neg1 ? 1 : 0) | (g.neg2 ? 2 : 0);
 }
 
 // small multiple k * P, k < 2^24, by double-and-add (MSB first)
@@ -417,10 +458,13 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
             void *out) {
   constexpr size_t PB = 3 * field_traits<F>::bytes;
   if (n_shards < 1 || shard < 0 || shard >= n_shards) return B200_EINVAL;
-  if (n >= ((size_t)1 << 31)) return B200_EINVAL;
+  if (n >= ((size_t)1 << 30)) return B200_EINVAL;
   msm_plan pl;
-  pl.c = ctx->msm_c ? ctx->msm_c : auto_window(n);
-  pl.nwin = (256 + pl.c - 1) / pl.c;
+  // GLV (G1 only): 2n entries with 127-bit sub-scalars -> ceil(128/c) windows instead of ceil(256/c)
+  pl.glv = (sizeof(F) == sizeof(fp) && (ctx->tune_g1_glv == 1 || (ctx->tune_g1_glv == 2 && n_shards > 1))) ? 1 : 0;
+  pl.c = ctx->msm_c ? ctx->msm_c : auto_window(pl.glv ? 2 * n : n);
+  pl.nwin = ((pl.glv ? 128 : 256) + pl.c - 1) / pl.c;
+  const size_t sstride = pl.glv ? 2 * n : n;  // entries per window
   if (pl.nwin > MAX_WINDOWS) return B200_EINVAL;
   pl.nbuckets = 1 << (pl.c - 1);
   pl.nloc = 0;
@@ -437,8 +481,9 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
   int chunk = (pl.nbuckets + chunks - 1) / chunks;
   if (chunk < 1) chunk = 1;
   int blocks_per_window = chunks / RB;
-  size_t need = 4 * arena_pad(total * 4) + 3 * arena_pad(4 * SIZE_BINS * 4) + arena_pad((size_t)pl.nloc * n * 4) +
-                arena_pad(total * PB) + arena_pad((size_t)pl.nloc * blocks_per_window * PB) + arena_pad(PB) + 4096;
+  size_t need = 4 * arena_pad(total * 4) + 3 * arena_pad(4 * SIZE_BINS * 4) + arena_pad((size_t)pl.nloc * sstride * 4) +
+                arena_pad(total * PB) + arena_pad((size_t)pl.nloc * blocks_per_window * PB) + arena_pad(PB) +
+                (pl.glv ? arena_pad(48 * n) : 0) + 4096;
   int rc = arena_reserve(ctx, need);
   if (rc != B200_OK) return rc;
   uint32_t *hist = arena_take<uint32_t>(ctx, total);
@@ -447,10 +492,12 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
   uint32_t *size_hist = arena_take<uint32_t>(ctx, 4 * SIZE_BINS);   // [parity][hist | cursor]
   uint32_t *size_base = arena_take<uint32_t>(ctx, 2 * SIZE_BINS);   // [parity]
   uint32_t *order = arena_take<uint32_t>(ctx, total);
-  uint32_t *sorted = arena_take<uint32_t>(ctx, (size_t)pl.nloc * n);
+  uint32_t *sorted = arena_take<uint32_t>(ctx, (size_t)pl.nloc * sstride);
   char *buckets = arena_take<char>(ctx, total * PB);
   char *partials = arena_take<char>(ctx, (size_t)pl.nloc * blocks_per_window * PB);
   char *hacc = arena_take<char>(ctx, PB);
+  char *bx = pl.glv ? arena_take<char>(ctx, 48 * n) : nullptr;
+  if (pl.glv) B200_LAUNCH(ctx, k_msm_glv_bx, nblk(n, 256), 256, 0, (const char *)points, n, bx);
   // hist and cursor are adjacent: one memset
   B200_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)((char *)offsets - (char *)hist), ctx->stream));
   // Window groups, top-down.  A group = consecutive local windows = a contiguous range of slots.
@@ -487,7 +534,7 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
     B200_LAUNCH_ON(ctx, st, k_msm_count, nblk(n, 256), 256, 0, pg, (const uint32_t *)scalars, (const uint8_t *)inf, n, hist + s0);
     B200_LAUNCH_ON(ctx, st, k_msm_scan, cnt, 1024, 0, pl.nbuckets, hist + s0, offsets + s0);
     B200_LAUNCH_ON(ctx, st, k_msm_scatter, nblk(n, 256), 256, 0, pg, (const uint32_t *)scalars, (const uint8_t *)inf, n,
-                   offsets + s0, cursor + s0, sorted + (size_t)j_lo * n);
+                   sstride, offsets + s0, cursor + s0, sorted + (size_t)j_lo * sstride);
     return B200_OK;
   };
   {
@@ -509,20 +556,20 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
     if constexpr (sizeof(F) == sizeof(fp)) {
       if (ctx->tune_g1_prefetch) {
       B200_LAUNCH(ctx, (k_msm_accumulate<F, 3, true>), nblk(gtotal, 128), 128, 2 * 2 * field_traits<F>::bytes * 128, pl.nbuckets,
-                  gtotal, s0, (const char *)points, n, offsets, hist, sorted, order + s0, buckets);
+                  gtotal, s0, (const char *)points, bx, sstride, offsets, hist, sorted, order + s0, buckets);
       } else {
-      B200_LAUNCH(ctx, (k_msm_accumulate<F, 3, false>), nblk(gtotal, 128), 128, 0, pl.nbuckets, gtotal, s0, (const char *)points, n,
-                  offsets, hist, sorted, order + s0, buckets);
+      B200_LAUNCH(ctx, (k_msm_accumulate<F, 3, false>), nblk(gtotal, 128), 128, 0, pl.nbuckets, gtotal, s0, (const char *)points,
+                  bx, sstride, offsets, hist, sorted, order + s0, buckets);
       }
     } else if (ctx->tune_g2_acc_blocks == 2) {   // accumulator in registers: 255 regs, 2 blocks/SM
-      B200_LAUNCH(ctx, (k_msm_accumulate<F, 2, false>), nblk(gtotal, 128), 128, 0, pl.nbuckets, gtotal, s0, (const char *)points, n,
-                  offsets, hist, sorted, order + s0, buckets);
+      B200_LAUNCH(ctx, (k_msm_accumulate<F, 2, false>), nblk(gtotal, 128), 128, 0, pl.nbuckets, gtotal, s0, (const char *)points,
+                  (const char *)nullptr, sstride, offsets, hist, sorted, order + s0, buckets);
     } else if (ctx->tune_g2_acc_blocks == 3) {   // accumulator in shared memory, built for 3 blocks/SM
       B200_LAUNCH(ctx, (k_msm_accumulate_g2sm<3>), nblk(gtotal, 128), 128, 96 * 128 * 4, pl.nbuckets, gtotal, s0,
-                  (const char *)points, n, offsets, hist, sorted, order + s0, buckets);
+                  (const char *)points, sstride, offsets, hist, sorted, order + s0, buckets);
     } else {                                     // accumulator in shared memory, 2 blocks/SM (255 regs)
       B200_LAUNCH(ctx, (k_msm_accumulate_g2sm<2>), nblk(gtotal, 128), 128, 96 * 128 * 4, pl.nbuckets, gtotal, s0,
-                  (const char *)points, n, offsets, hist, sorted, order + s0, buckets);
+                  (const char *)points, sstride, offsets, hist, sorted, order + s0, buckets);
     }
     B200_CUDA(ctx, cudaEventRecord(ctx->ev_sync[1 + 2 * g], ctx->stream));
     if (g + 1 < ng) {  // sort the next group under this group's accumulate
@@ -592,6 +639,20 @@ int b200_g2_msm_shard_dev(b200_ctx *ctx, const void *points, const void *inf, co
   if (!out || (n && (!points || !scalars))) return B200_EINVAL;
   int rc = msm_dev<fp2>(ctx, points, inf, scalars, n, shard, n_shards, out);
   if (rc != B200_OK) return rc;
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+int b200_glv_decompose(b200_ctx *ctx, const b200_scalar *scalars, size_t n, uint8_t *k1k2, uint8_t *signs) {
+  CHECK_CTX(ctx);
+  if (n && (!scalars || !k1k2 || !signs)) return B200_EINVAL;
+  if (n == 0) return B200_OK;
+  int rc = stage_reserve(ctx, 32 * n + 32 * n + n + 1024);
+  if (rc != B200_OK) return rc;
+  void *ds = stage_take(ctx, 32 * n), *dk = stage_take(ctx, 32 * n), *dg = stage_take(ctx, n);
+  B200_CUDA(ctx, cudaMemcpyAsync(ds, scalars, 32 * n, cudaMemcpyHostToDevice, ctx->stream));
+  B200_LAUNCH(ctx, k_glv_decompose, nblk(n, 128), 128, 0, (const uint32_t *)ds, n, (uint32_t *)dk, (uint8_t *)dg);
+  B200_CUDA(ctx, cudaMemcpyAsync(k1k2, dk, 32 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  B200_CUDA(ctx, cudaMemcpyAsync(signs, dg, n, cudaMemcpyDeviceToHost, ctx->stream));
   B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return B200_OK;
 }

@@ -161,6 +161,20 @@ class Engine:
         self._ck(getattr(self.lib, self._g(k) + "msm")(self.h, _hp(xy), _hp(inf), _hp(s), xy.shape[0], _hp(out)), "msm")
         return out
 
+    def glv_decompose(self, s):
+        """(k1, k2) signed Python ints per scalar with k = k1 + k2*lambda (mod q) — test surface of csrc/glv.cuh"""
+        s = _np(s, np.uint8, 32)
+        n = s.shape[0]
+        kk = np.empty((n, 32), np.uint8)
+        sg = np.empty(n, np.uint8)
+        self._ck(self.lib.b200_glv_decompose(self.h, _hp(s), n, _hp(kk), _hp(sg)), "glv_decompose")
+        out = []
+        for i in range(n):
+            k1 = int.from_bytes(kk[i, :16].tobytes(), "little")
+            k2 = int.from_bytes(kk[i, 16:].tobytes(), "little")
+            out.append((-k1 if sg[i] & 1 else k1, -k2 if sg[i] & 2 else k2))
+        return out
+
     # ---------------------------------------------------------------- (de)serialization (SURVEY §8f rows 1-2)
     def serialize(self, k, xy, inf=None, compressed=True):
         """G{k}Affine::to_compressed / to_uncompressed for a batch -> (n, 48k | 96k) uint8"""

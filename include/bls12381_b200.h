@@ -69,7 +69,7 @@ uint64_t b200_ctx_launch_count(const b200_ctx *ctx);
  * '\n' into `names`, and returns the number of records since the last set_timing call (>= 0). */
 int b200_ctx_set_timing(b200_ctx *ctx, int on);
 int b200_ctx_get_timing(b200_ctx *ctx, char *names, size_t names_len, float *ms, int max);
-/* tuning knobs by name: "msm_window" (0 = auto, else 2..24), "g2_acc_blocks" (G2 bucket kernel variant: 2 registers,
+/* tuning knobs by name: "msm_window" (0 = auto, else 2..24), "g1_glv" (0 off, 1 on, 2 auto = on for window-sharded calls), "g1_prefetch" (0|1), "g2_acc_blocks" (G2 bucket kernel variant: 2 registers,
  * 3 shared-memory accumulator built for 3 blocks/SM, 4 shared-memory accumulator at 2 blocks/SM = default), "pairing_blocks" (4|8), "pairing_chunks" (1..64 independent chunks of a
  * pairing batch in flight).  Unknown key or bad value -> B200_EINVAL. */
 int b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int value);
@@ -156,6 +156,11 @@ int b200_final_exponentiation_batch_dev(b200_ctx *ctx, const void *in, size_t n,
 int b200_pairing_batch_dev(b200_ctx *ctx, const void *p, const void *p_inf, const void *q, const void *q_inf, size_t n, void *gt_out);
 /* out = product of the n Fp12 values (MillerLoopResult `+`, src/pairings.rs:179-186) */
 int b200_fp12_product_dev(b200_ctx *ctx, const void *in, size_t n, void *out);
+
+/* test surface for the GLV scalar decomposition used by the G1 MSM (csrc/glv.cuh): k = k1 + k2*lambda (mod q),
+ * |k1|, |k2| < 2^127.  k1k2[i] = k1 magnitude (16 B LE) | k2 magnitude (16 B LE); signs[i] bit 0 = k1 < 0,
+ * bit 1 = k2 < 0. */
+int b200_glv_decompose(b200_ctx *ctx, const b200_scalar *scalars, size_t n, uint8_t *k1k2, uint8_t *signs);
 
 /* ---- measurement helper: dependent-free IMAD.WIDE.U32 stream on all SMs; returns achieved
  * 32x32+64 multiply-adds per second (the integer roofline denominator) ------------ */

@@ -298,3 +298,38 @@ def test_g2_msm_bucket_kernel_variants(eng, orc, mode):
         _msm_case(eng, orc, k, xy, inf, s, cs=(0, 6, 12))
     finally:
         eng.set_tuning("g2_acc_blocks", 4)
+
+
+def test_glv_decompose(eng):
+    """k = k1 + k2*lambda (mod q) with |k1|, |k2| < 2^127 for random and extreme scalars (csrc/glv.cuh)"""
+    z = 0xd201000000010000
+    lam = z * z - 1
+    assert lam * lam + lam + 1 == pyref.Q
+    rng = np.random.default_rng(77)
+    vals = [0, 1, 2, pyref.Q - 1, pyref.Q - 2, lam, lam + 1, lam - 1, pyref.Q // 2, pyref.Q // 2 + 1, (pyref.Q + 1) // 2 - 1,
+            lam * lam, lam * (lam // 2), (lam // 2) * (lam + 1), 1 << 254, pyref.Q - lam, lam // 2, lam // 2 + 1,
+            (lam // 2) * lam + lam // 2, (lam // 2 + 1) * lam - 1, (1 << 128) - 1, 1 << 128, 1 << 127]
+    vals += [int.from_bytes(rng.bytes(40), "little") % pyref.Q for _ in range(4000)]
+    s = np.stack([util.scalar_bytes(v) for v in vals])
+    for v, (k1, k2) in zip(vals, eng.glv_decompose(s)):
+        assert (k1 + k2 * lam - v) % pyref.Q == 0, hex(v)
+        assert abs(k1) < (1 << 127) and abs(k2) < (1 << 127), hex(v)
+
+
+@pytest.mark.parametrize("glv", [0, 1])
+def test_g1_msm_with_and_without_glv(eng, orc, glv):
+    rng = np.random.default_rng(1200)
+    _, xy, inf = util.rand_points(orc, 1, rng, 700)
+    s = util.rand_scalars(rng, 700)
+    s[0] = 0
+    s[1] = util.scalar_bytes(pyref.Q - 1)
+    s[2] = util.scalar_bytes(0xac45a4010001a40200000000ffffffff)          # lambda itself
+    s[3] = util.scalar_bytes(0xac45a4010001a40200000000ffffffff + 1)
+    xy[5], s[5] = xy[4], s[4]
+    inf[6] = 1
+    eng.set_tuning("g1_glv", glv)
+    try:
+        _msm_case(eng, orc, 1, xy, inf, s, cs=(0, 5, 8, 13, 16))
+        _msm_case(eng, orc, 1, xy[:3], inf[:3], s[:3], cs=(0, 4))
+    finally:
+        eng.set_tuning("g1_glv", 2)
