@@ -22,10 +22,12 @@ struct b200_ctx {
   uint64_t launches = 0;
   int msm_c = 0;
   int tune_pairing_blocks = 4; // resident 64-thread blocks/SM the pairing kernels are compiled for (4: 255 regs, measured best; 8: 128 regs, spills)
-  // G1 MSM: GLV split k = k1 + k2*lambda (8 windows of 2n entries instead of 16 of n).  0 off, 1 on, 2 auto = on for
-  // window-sharded calls (n_shards > 1: halves each shard's bucket-reduction + Horner tail), off for a whole MSM on
-  // one GPU (measured 9.34 vs 9.02 ms at 2^20: fewer, fatter windows pipeline worse and phi(P) costs extra reads)
-  int tune_g1_glv = 2;
+  // G1 MSM: GLV split k = k1 + k2*lambda (8 windows of 2n entries instead of 16 of n).  0 off (default), 1 on,
+  // 2 = on for window-sharded calls only.  Implemented, parity-tested, and measured NEGATIVE at 2^20 on B200:
+  // 1 GPU 9.34 vs 9.02 ms, 8 GPUs 3.66 vs 3.19 ms — halving the windows halves the (window x bucket) slots, i.e. the
+  // thread-level parallelism of the bucket kernel (one 2^15-bucket window = 0.58 of a wave), which costs more than
+  // the shorter reduction/Horner tail saves.  Kept as a knob for larger n / wider windows.
+  int tune_g1_glv = 0;
   int tune_g1_prefetch = 1;    // G1 bucket kernel: cp.async double-buffered prefetch of the next point (1) or plain loads (0)
   int tune_pairing_chunks = 4; // independent Miller+final-exp chunks of a pairing batch kept in flight on 2 streams
   // G2 bucket kernel: 2 = accumulator in registers (255 regs, 2 blocks/SM); 3 = accumulator in shared memory, built

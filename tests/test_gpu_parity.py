@@ -332,4 +332,4 @@ def test_g1_msm_with_and_without_glv(eng, orc, glv):
         _msm_case(eng, orc, 1, xy, inf, s, cs=(0, 5, 8, 13, 16))
         _msm_case(eng, orc, 1, xy[:3], inf[:3], s[:3], cs=(0, 4))
     finally:
-        eng.set_tuning("g1_glv", 2)
+        eng.set_tuning("g1_glv", 0)
