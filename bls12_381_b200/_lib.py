@@ -34,6 +34,10 @@ SIGNATURES = {
     "b200_final_exponentiation_batch_dev": [_vp, _vp, _sz, _vp],
     "b200_pairing_batch_dev": [_vp, _vp, _vp, _vp, _vp, _sz, _vp],
     "b200_fp12_product_dev": [_vp, _vp, _sz, _vp],
+    "b200_g2_prepare": [_vp, _vp, _vp, _sz, _vp],
+    "b200_multi_miller_loop_prepared": [_vp, _vp, _vp, _vp, _vp, _sz, _vp],
+    "b200_g2_prepare_dev": [_vp, _vp, _vp, _sz, _vp],
+    "b200_miller_loop_prepared_batch_dev": [_vp, _vp, _vp, _vp, _vp, _sz, _vp],
 }
 for _g in ("g1", "g2"):
     SIGNATURES.update({
@@ -48,6 +52,7 @@ for _g in ("g1", "g2"):
         "b200_%s_msm_dev" % _g: [_vp, _vp, _vp, _vp, _sz, _vp],
         "b200_%s_msm_shard_dev" % _g: [_vp, _vp, _vp, _vp, _sz, _i, _i, _vp],
         "b200_%s_sum_dev" % _g: [_vp, _vp, _sz, _vp],
+        "b200_%s_check" % _g: [_vp, _vp, _vp, _sz, _vp],
         "b200_%s_serialize" % _g: [_vp, _vp, _vp, _sz, _i, _vp],
         "b200_%s_deserialize" % _g: [_vp, _vp, _sz, _i, _vp, _vp, _vp],
     })

@@ -9,7 +9,10 @@ using namespace b200;
   int b200_pair_miller_##v(b200_ctx *, cudaStream_t, const void *, const void *, const void *, const void *, size_t,   \
                            void *);                                                                                    \
   int b200_pair_final_exp_##v(b200_ctx *, cudaStream_t, const void *, size_t, void *);                                 \
-  int b200_pair_product_##v(b200_ctx *, const void *, size_t, void *);
+  int b200_pair_product_##v(b200_ctx *, const void *, size_t, void *);                                                 \
+  int b200_pair_g2_prepare_##v(b200_ctx *, cudaStream_t, const void *, const void *, size_t, void *);                  \
+  int b200_pair_miller_prepared_##v(b200_ctx *, cudaStream_t, const void *, const void *, const void *, const void *,  \
+                                    size_t, void *);
 DECL_VARIANT(v4) DECL_VARIANT(v8)
 
 namespace {
@@ -119,6 +122,57 @@ int b200_fp12_product_dev(b200_ctx *ctx, const void *in, size_t n, void *out) {
   if (!out || (n && !in)) return B200_EINVAL;
   int rc = product_dev(ctx, in, n, out);
   return rc != B200_OK ? rc : sync(ctx);
+}
+
+// ---- G2Prepared: prepared coefficients stay resident on the device for fixed verifying keys
+int b200_g2_prepare_dev(b200_ctx *ctx, const void *q, const void *q_inf, size_t n, void *coeffs) {
+  CHECK_CTX(ctx);
+  if (n && (!q || !coeffs)) return B200_EINVAL;
+  int rc = b200_pair_g2_prepare_v4(ctx, ctx->stream, q, q_inf, n, coeffs);
+  return rc != B200_OK ? rc : sync(ctx);
+}
+int b200_miller_loop_prepared_batch_dev(b200_ctx *ctx, const void *p, const void *p_inf, const void *coeffs,
+                                        const void *q_inf, size_t n, void *out) {
+  CHECK_CTX(ctx);
+  if (n && (!p || !coeffs || !out)) return B200_EINVAL;
+  int rc = b200_pair_miller_prepared_v4(ctx, ctx->stream, p, p_inf, coeffs, q_inf, n, out);
+  return rc != B200_OK ? rc : sync(ctx);
+}
+int b200_g2_prepare(b200_ctx *ctx, const b200_g2_affine *q, const uint8_t *q_inf, size_t n, b200_fp2 *coeffs) {
+  CHECK_CTX(ctx);
+  if (n && (!q || !coeffs)) return B200_EINVAL;
+  if (n == 0) return B200_OK;
+  int rc = stage_reserve(ctx, 192 * n + n + 19584 * n + 1024);
+  if (rc != B200_OK) return rc;
+  void *dq = stage_take(ctx, 192 * n), *dqi = q_inf ? stage_take(ctx, n) : nullptr, *dc = stage_take(ctx, 19584 * n);
+  B200_CUDA(ctx, cudaMemcpyAsync(dq, q, 192 * n, cudaMemcpyHostToDevice, ctx->stream));
+  if (q_inf) B200_CUDA(ctx, cudaMemcpyAsync(dqi, q_inf, n, cudaMemcpyHostToDevice, ctx->stream));
+  rc = b200_pair_g2_prepare_v4(ctx, ctx->stream, dq, dqi, n, dc);
+  if (rc != B200_OK) return rc;
+  B200_CUDA(ctx, cudaMemcpyAsync(coeffs, dc, 19584 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  return sync(ctx);
+}
+// multi_miller_loop(&[(&p_i, &prepared_i)]) -> ONE MillerLoopResult  (src/pairings.rs:554-603)
+int b200_multi_miller_loop_prepared(b200_ctx *ctx, const b200_g1_affine *p, const uint8_t *p_inf, const b200_fp2 *coeffs,
+                                    const uint8_t *q_inf, size_t n, b200_fp12 *out) {
+  CHECK_CTX(ctx);
+  if (!out || (n && (!p || !coeffs))) return B200_EINVAL;
+  int rc = stage_reserve(ctx, 96 * n + 2 * n + 19584 * n + 576 * (n + 2) + 2048);
+  if (rc != B200_OK) return rc;
+  void *dp = stage_take(ctx, 96 * (n ? n : 1)), *dpi = p_inf ? stage_take(ctx, n ? n : 1) : nullptr;
+  void *dqi = q_inf ? stage_take(ctx, n ? n : 1) : nullptr, *dc = stage_take(ctx, 19584 * (n ? n : 1));
+  void *dml = stage_take(ctx, 576 * (n ? n : 1)), *dout = stage_take(ctx, 576);
+  if (n) {
+    B200_CUDA(ctx, cudaMemcpyAsync(dp, p, 96 * n, cudaMemcpyHostToDevice, ctx->stream));
+    if (p_inf) B200_CUDA(ctx, cudaMemcpyAsync(dpi, p_inf, n, cudaMemcpyHostToDevice, ctx->stream));
+    if (q_inf) B200_CUDA(ctx, cudaMemcpyAsync(dqi, q_inf, n, cudaMemcpyHostToDevice, ctx->stream));
+    B200_CUDA(ctx, cudaMemcpyAsync(dc, coeffs, 19584 * n, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  rc = b200_pair_miller_prepared_v4(ctx, ctx->stream, dp, dpi, dc, dqi, n, dml);
+  if (rc == B200_OK) rc = product_dev(ctx, dml, n, dout);
+  if (rc != B200_OK) return rc;
+  B200_CUDA(ctx, cudaMemcpyAsync(out, dout, 576, cudaMemcpyDeviceToHost, ctx->stream));
+  return sync(ctx);
 }
 
 int b200_miller_loop_batch(b200_ctx *ctx, const b200_g1_affine *p, const uint8_t *p_inf, const b200_g2_affine *q,

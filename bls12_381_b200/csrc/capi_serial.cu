@@ -6,8 +6,8 @@
 // Wire format: src/notes/serialization.rs:1-29 — Fp big-endian 48 bytes (Fp::to_bytes src/fp.rs:211-227,
 // from_bytes :179-208 with its canonicity check), Fp2 as c1 || c0, flag bits 7/6/5 of byte 0 =
 // compressed / infinity / lexicographically-largest-y.  The subgroup check (is_torsion_free) is NOT part of
-// these entry points (out of scope this round); `status` reports what the reference's *_unchecked
-// constructors report plus the on-curve test.
+// the deserialize entry points; it is offered separately (b200_g{1,2}_check = is_on_curve + is_torsion_free,
+// src/g1.rs:401-418, src/g2.rs:475-491), so deserialize + check == the reference's checked constructors.
 #include "constants.cuh"
 #include "ctx.cuh"
 #include "curve.cuh"
@@ -143,6 +143,51 @@ B200_DEV bool on_curve(const F &x, const F &y) {  // y^2 - x^3 == b   (src/g1.rs
   return f_eq(f_sub(f_sqr(y), f_mul(f_sqr(x), x)), curve_b<F>());
 }
 
+// ---- subgroup membership (the check the reference's checked constructors add: src/g1.rs:264-267, :336)
+// [x]P for the BLS parameter x = -0xd201000000010000 (src/g1.rs:777-793, src/g2.rs:915-932)
+template <class F>
+B200_DEV proj<F> proj_mul_by_x(const proj<F> &s) {
+  proj<F> xself = proj_identity<F>(), acc = s;
+  unsigned long long x = 0xd201000000010000ull >> 1;
+#pragma unroll 1
+  while (x != 0) {
+    acc = proj_double(acc);
+    if (x & 1) xself = proj_add(xself, acc);
+    x >>= 1;
+  }
+  return proj_neg(xself);
+}
+template <class F>
+B200_DEV bool proj_eq(const proj<F> &a, const proj<F> &b) {  // src/g1.rs:479-496
+  bool az = f_is_zero(a.z), bz = f_is_zero(b.z);
+  if (az || bz) return az && bz;
+  return f_eq(f_mul(a.x, b.z), f_mul(b.x, a.z)) && f_eq(f_mul(a.y, b.z), f_mul(b.y, a.z));
+}
+// G1: endomorphism(P) == -[x^2]P   (src/g1.rs:401-410, eprint 2021/1130 sec. 6)
+B200_DEV bool torsion_free(const affine<fp> &p) {
+  proj<fp> pp = proj_from_affine(p);
+  proj<fp> m = proj_neg(proj_mul_by_x(proj_mul_by_x(pp)));
+  proj<fp> e = pp;
+  e.x = fp_mul_c(e.x, fp_const(K_G1_BETA_REF));
+  return proj_eq(m, e);
+}
+// G2: psi(P) == [x]P   (src/g2.rs:475-482, psi :847-888)
+B200_DEV bool torsion_free(const affine<fp2> &p) {
+  proj<fp2> pp = proj_from_affine(p);
+  fp2 cx = fp2{fp_zero(), fp_const(K_PSI_X_U)}, cy = fp2{fp_const(K_PSI_Y_R), fp_const(K_PSI_Y_U)};
+  proj<fp2> psi{M2(fp2_conj(pp.x), cx), M2(fp2_conj(pp.y), cy), fp2_conj(pp.z)};
+  return proj_eq(psi, proj_mul_by_x(pp));
+}
+// status bit 0: is_on_curve, bit 1: is_torsion_free
+template <class F>
+__global__ void __launch_bounds__(128) k_point_checks(const char *xy, const uint8_t *inf, size_t n, uint8_t *status) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  affine<F> p = affine_load<F>(xy, inf, i);
+  bool oc = p.inf || on_curve(p.x, p.y);
+  status[i] = (oc ? 1 : 0) | (torsion_free(p) ? 2 : 0);
+}
+
 template <class F>
 __global__ void __launch_bounds__(128) k_serialize(const char *xy, const uint8_t *inf, size_t n, int compressed,
                                                  uint8_t *out) {
@@ -237,6 +282,20 @@ int deserialize_host(b200_ctx *ctx, const uint8_t *in, size_t n, int compressed,
   return B200_OK;
 }
 
+template <class F>
+int checks_host(b200_ctx *ctx, const void *xy, const uint8_t *inf, size_t n, uint8_t *status) {
+  constexpr size_t FB = field_traits<F>::bytes;
+  int rc = stage_reserve(ctx, 2 * FB * n + 2 * n + 8 * 256);
+  if (rc != B200_OK) return rc;
+  void *dxy = stage_take(ctx, 2 * FB * n), *di = inf ? stage_take(ctx, n) : nullptr, *ds = stage_take(ctx, n);
+  B200_CUDA(ctx, cudaMemcpyAsync(dxy, xy, 2 * FB * n, cudaMemcpyHostToDevice, ctx->stream));
+  if (inf) B200_CUDA(ctx, cudaMemcpyAsync(di, inf, n, cudaMemcpyHostToDevice, ctx->stream));
+  B200_LAUNCH(ctx, k_point_checks<F>, nblk(n, 128), 128, 0, (const char *)dxy, (const uint8_t *)di, n, (uint8_t *)ds);
+  B200_CUDA(ctx, cudaMemcpyAsync(status, ds, n, cudaMemcpyDeviceToHost, ctx->stream));
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
 }  // namespace
 
 #define CHECK_CTX(ctx)                      \
@@ -267,6 +326,17 @@ int b200_g2_deserialize(b200_ctx *ctx, const uint8_t *in, size_t n, int compress
   CHECK_CTX(ctx);
   if (n && (!in || !out || !out_inf || !status)) return B200_EINVAL;
   return n ? deserialize_host<fp2>(ctx, in, n, compressed != 0, out, out_inf, status) : B200_OK;
+}
+
+int b200_g1_check(b200_ctx *ctx, const b200_g1_affine *p, const uint8_t *inf, size_t n, uint8_t *status) {
+  CHECK_CTX(ctx);
+  if (n && (!p || !status)) return B200_EINVAL;
+  return n ? checks_host<fp>(ctx, p, inf, n, status) : B200_OK;
+}
+int b200_g2_check(b200_ctx *ctx, const b200_g2_affine *p, const uint8_t *inf, size_t n, uint8_t *status) {
+  CHECK_CTX(ctx);
+  if (n && (!p || !status)) return B200_EINVAL;
+  return n ? checks_host<fp2>(ctx, p, inf, n, status) : B200_OK;
 }
 
 }  // extern "C"

@@ -122,6 +122,72 @@ B200_DEV void miller_loop_pair(fp12 *f, const affine<fp> &pin, const affine<fp2>
   if (either) fp12_set_one(f);
 }
 
+// ---- G2Prepared (src/pairings.rs:498-546): the 68 line-coefficient triples of Q, in the order the Miller loop
+// consumes them.  Memory layout per Q: 68 x (a, b, c) Fp2 = 68 x 288 B = 19 584 B.  The identity is prepared as
+// the generator's coefficients (the caller keeps the infinity flag, :528-544).
+B200_DEV void g2_prepare(const affine<fp2> &qin, char *coeffs) {
+  fp2 qx = qin.inf ? fp2{fp_const(K_G2_GEN_X0), fp_const(K_G2_GEN_X1)} : qin.x;
+  fp2 qy = qin.inf ? fp2{fp_const(K_G2_GEN_Y0), fp_const(K_G2_GEN_Y1)} : qin.y;
+  proj<fp2> cur{qx, qy, fp2_one()};
+  line_coeffs co;
+  int idx = 0;
+  auto emit = [&]() {
+    fp2_store(coeffs + 288 * idx, co.a);
+    fp2_store(coeffs + 288 * idx + 96, co.b);
+    fp2_store(coeffs + 288 * idx + 192, co.c);
+    idx++;
+  };
+  const unsigned long long x = B200_BLS_X >> 1;
+  bool found_one = false;
+#pragma unroll 1
+  for (int b = 63; b >= 0; b--) {
+    bool bit = (x >> b) & 1;
+    if (!found_one) {
+      found_one = bit;
+      continue;
+    }
+    pairing_doubling_step(&cur, &co);
+    emit();
+    if (bit) {
+      pairing_addition_step(&cur, &qx, &qy, &co);
+      emit();
+    }
+  }
+  pairing_doubling_step(&cur, &co);
+  emit();
+}
+// One term of multi_miller_loop over prepared coefficients (src/pairings.rs:554-603 with a single term):
+// f <- conj( ... (f^2 * ell(coeffs[i], p)) ... ).  A term with p or q at infinity contributes one() (:566-569).
+B200_DEV void miller_loop_prepared(fp12 *f, const affine<fp> &p, const char *coeffs, bool q_inf) {
+  fp12_set_one(f);
+  if (p.inf || q_inf) return;
+  fp px = p.x, py = p.y;
+  line_coeffs co;
+  int idx = 0;
+  auto step = [&]() {
+    co.a = fp2_load(coeffs + 288 * idx);
+    co.b = fp2_load(coeffs + 288 * idx + 96);
+    co.c = fp2_load(coeffs + 288 * idx + 192);
+    idx++;
+    pairing_ell(f, &co, &px, &py);
+  };
+  const unsigned long long x = B200_BLS_X >> 1;
+  bool found_one = false;
+#pragma unroll 1
+  for (int b = 63; b >= 0; b--) {
+    bool bit = (x >> b) & 1;
+    if (!found_one) {
+      found_one = bit;
+      continue;
+    }
+    step();
+    if (bit) step();
+    fp12_sqr(f, f);
+  }
+  step();
+  fp12_conj(f, f);
+}
+
 // src/pairings.rs:50-62
 B200_DEV void fp4_square(fp2 *c0, fp2 *c1, const fp2 &a, const fp2 &b) {
   fp2 t0 = S2(a), t1 = S2(b);

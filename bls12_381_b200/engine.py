@@ -185,6 +185,14 @@ class Engine:
                                                             _hp(out)), "serialize")
         return out
 
+    def check(self, k, xy, inf=None):
+        """per point: bit 0 = is_on_curve, bit 1 = is_torsion_free (src/g1.rs:401-418, src/g2.rs:475-491)"""
+        xy = _np(xy, np.uint64, self.AFF[k])
+        inf = None if inf is None else _np(inf, np.uint8)
+        st = np.empty(xy.shape[0], np.uint8)
+        self._ck(getattr(self.lib, self._g(k) + "check")(self.h, _hp(xy), _hp(inf), xy.shape[0], _hp(st)), "check")
+        return st
+
     def deserialize(self, k, data, compressed=True):
         """from_{un,}compressed_unchecked + is_on_curve -> (xy, inf, status); status bit0 = Some, bit1 = on curve"""
         data = _np(data, np.uint8, (48 if compressed else 96) * k)
@@ -231,6 +239,33 @@ class Engine:
         self._ck(self.lib.b200_multi_miller_loop(self.h, _hp(pxy), _hp(pinf), _hp(qxy), _hp(qinf), pxy.shape[0],
                                                  _hp(out)), "multi_miller_loop")
         return out
+
+    def g2_prepare(self, qxy, qinf=None):
+        """G2Prepared::from for a batch -> (n, 68, 36) uint64 line coefficients (src/pairings.rs:504-546)"""
+        qxy = _np(qxy, np.uint64, 24)
+        qinf = None if qinf is None else _np(qinf, np.uint8)
+        out = np.empty((qxy.shape[0], 68, 36), np.uint64)
+        self._ck(self.lib.b200_g2_prepare(self.h, _hp(qxy), _hp(qinf), qxy.shape[0], _hp(out)), "g2_prepare")
+        return out
+
+    def multi_miller_loop_prepared(self, pxy, pinf, coeffs, qinf=None):
+        pxy = _np(pxy, np.uint64, 12)
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.uint64).reshape(-1, 68, 36)
+        if coeffs.shape[0] != pxy.shape[0]:
+            raise ValueError("p/prepared length mismatch")
+        pinf = None if pinf is None else _np(pinf, np.uint8)
+        qinf = None if qinf is None else _np(qinf, np.uint8)
+        out = np.empty((1, 72), np.uint64)
+        self._ck(self.lib.b200_multi_miller_loop_prepared(self.h, _hp(pxy), _hp(pinf), _hp(coeffs), _hp(qinf), pxy.shape[0],
+                                                          _hp(out)), "multi_miller_loop_prepared")
+        return out
+
+    def g2_prepare_dev(self, q, qinf, n, coeffs):
+        self._ck(self.lib.b200_g2_prepare_dev(self.h, _dp(q), _dp(qinf), n, _dp(coeffs)), "g2_prepare_dev")
+
+    def miller_loop_prepared_batch_dev(self, p, pinf, coeffs, qinf, n, out):
+        self._ck(self.lib.b200_miller_loop_prepared_batch_dev(self.h, _dp(p), _dp(pinf), _dp(coeffs), _dp(qinf), n, _dp(out)),
+                 "miller_loop_prepared_batch_dev")
 
     # ---------------------------------------------------------------- device-pointer entry points (torch tensors)
     def mul_batch_dev(self, k, p, s, out, n):

@@ -123,14 +123,26 @@ int b200_pairing_batch(b200_ctx *ctx, const b200_g1_affine *p, const uint8_t *p_
  * the limbs are bit-identical; identity terms contribute one(), like the reference's skip :566-569. */
 int b200_multi_miller_loop(b200_ctx *ctx, const b200_g1_affine *p, const uint8_t *p_inf, const b200_g2_affine *q, const uint8_t *q_inf, size_t n, b200_fp12 *out);
 
+/* ---- G2Prepared (src/pairings.rs:498-546): coeffs = n x 68 x (Fp2, Fp2, Fp2) = 19 584 B per Q, in
+ * the order the Miller loop consumes them; the identity is prepared as the generator (the caller keeps q_inf, :528-544).
+ * b200_multi_miller_loop_prepared = multi_miller_loop(&[(&p_i, &prepared_i)]) (:554-603), limb-exact; terms with p_i or
+ * q_i at infinity contribute one().  The _dev variants keep the coefficients resident in HBM for fixed verifying keys. */
+int b200_g2_prepare(b200_ctx *ctx, const b200_g2_affine *q, const uint8_t *q_inf, size_t n, b200_fp2 *coeffs);
+int b200_multi_miller_loop_prepared(b200_ctx *ctx, const b200_g1_affine *p, const uint8_t *p_inf, const b200_fp2 *coeffs, const uint8_t *q_inf, size_t n, b200_fp12 *out);
+int b200_g2_prepare_dev(b200_ctx *ctx, const void *q, const void *q_inf, size_t n, void *coeffs);
+int b200_miller_loop_prepared_batch_dev(b200_ctx *ctx, const void *p, const void *p_inf, const void *coeffs, const void *q_inf, size_t n, void *out);
+
 /* ---- point (de)serialization on the device (wire format src/notes/serialization.rs) -----
  * serialize: out[i] = G1Affine::to_compressed (48 B) / to_uncompressed (96 B)  src/g1.rs:221-260
  *            (G2: 96 / 192 B, Fp2 as c1 || c0                                   src/g2.rs:254-299)
  * deserialize: G1Affine::from_compressed_unchecked / from_uncompressed_unchecked (src/g1.rs:275-390,
  *            src/g2.rs:313-464).  status[i] bit 0 = the reference constructor would return Some (canonical
  *            field encodings, consistent flags, x on the curve for compressed input); bit 1 = is_on_curve
- *            (src/g1.rs:414).  Rejected inputs yield the identity.  The subgroup test is_torsion_free is NOT
- *            performed by these entry points. */
+ *            (src/g1.rs:414).  Rejected inputs yield the identity.  The subgroup test is b200_g{1,2}_check. */
+/* status[i] bit 0 = G1Affine::is_on_curve (src/g1.rs:414), bit 1 = is_torsion_free (src/g1.rs:401-410: endomorphism(P) == -[x^2]P;
+ * G2 src/g2.rs:475-482: psi(P) == [x]P).  deserialize + check == from_compressed / from_uncompressed (checked). */
+int b200_g1_check(b200_ctx *ctx, const b200_g1_affine *p, const uint8_t *inf, size_t n, uint8_t *status);
+int b200_g2_check(b200_ctx *ctx, const b200_g2_affine *p, const uint8_t *inf, size_t n, uint8_t *status);
 int b200_g1_serialize(b200_ctx *ctx, const b200_g1_affine *p, const uint8_t *inf, size_t n, int compressed, uint8_t *out);
 int b200_g2_serialize(b200_ctx *ctx, const b200_g2_affine *p, const uint8_t *inf, size_t n, int compressed, uint8_t *out);
 int b200_g1_deserialize(b200_ctx *ctx, const uint8_t *in, size_t n, int compressed, b200_g1_affine *out, uint8_t *out_inf, uint8_t *status);

@@ -650,6 +650,33 @@ static inline void g1p_batch_normalize(const G1Projective *p, G1Affine *q, size_
 static inline bool g1a_is_on_curve(const G1Affine &p) {
   return p.infinity || fp_eq(fp_sub(fp_square(p.y), fp_mul(fp_square(p.x), p.x)), G1_B);
 }
+// src/g1.rs:777-793 : [x]P by double-and-add over BLS_X >> 1 starting from the doubled point, then negate (x < 0)
+static inline G1Projective g1p_mul_by_x(const G1Projective &s) {
+  G1Projective xself = g1p_identity();
+  u64 x = 0xd201000000010000ULL >> 1;
+  G1Projective tmp = s;
+  while (x != 0) {
+    tmp = g1p_double(tmp);
+    if (x % 2 == 1) xself = g1p_add(xself, tmp);
+    x >>= 1;
+  }
+  return g1p_neg(xself);
+}
+// src/g1.rs:479-496 (cross-multiplied comparison)
+static inline bool g1p_eq(const G1Projective &a, const G1Projective &b) {
+  Fp x1 = fp_mul(a.x, b.z), x2 = fp_mul(b.x, a.z), y1 = fp_mul(a.y, b.z), y2 = fp_mul(b.y, a.z);
+  bool az = fp_is_zero(a.z), bz = fp_is_zero(b.z);
+  return (az && bz) || (!az && !bz && fp_eq(x1, x2) && fp_eq(y1, y2));
+}
+// src/g1.rs:421-428 BETA ; :430-437 endomorphism ; :401-410 is_torsion_free: endomorphism(P) == -[x^2]P
+static const Fp G1_BETA = {{0x30f1361b798a64e8ULL, 0xf3b8ddab7ece5a2aULL, 0x16a8ca3ac61577f7ULL,
+                            0xc26a2ff874fd029bULL, 0x3636b76660701c6eULL, 0x051ba4ab241b6160ULL}};
+static inline bool g1a_is_torsion_free(const G1Affine &p) {
+  G1Projective m = g1p_neg(g1p_mul_by_x(g1p_mul_by_x(g1p_from_affine(p))));
+  G1Affine e = p;
+  e.x = fp_mul(e.x, G1_BETA);
+  return g1p_eq(m, g1p_from_affine(e));
+}
 // src/g1.rs:221-260
 static inline void g1a_to_compressed(const G1Affine &p, uint8_t out[48]) {
   fp_to_bytes(p.infinity ? fp_zero() : p.x, out);
@@ -866,6 +893,40 @@ static inline void g2p_batch_normalize(const G2Projective *p, G2Affine *q, size_
     q[i].infinity = 0;
     if (skip) q[i] = g2a_identity();
   }
+}
+// src/g2.rs:915-932
+static inline G2Projective g2p_mul_by_x(const G2Projective &s) {
+  G2Projective xself = g2p_identity();
+  u64 x = 0xd201000000010000ULL >> 1;
+  G2Projective acc = s;
+  while (x != 0) {
+    acc = g2p_double(acc);
+    if (x % 2 == 1) xself = g2p_add(xself, acc);
+    x >>= 1;
+  }
+  return g2p_neg(xself);
+}
+// src/g2.rs:847-888
+static inline G2Projective g2p_psi(const G2Projective &s) {
+  static const Fp2 cx = {{{0, 0, 0, 0, 0, 0}},
+                         {{0x890dc9e4867545c3ULL, 0x2af322533285a5d5ULL, 0x50880866309b7e2cULL, 0xa20d1b8c7e881024ULL,
+                           0x14e4f04fe2db9068ULL, 0x14e56d3f1564853aULL}}};
+  static const Fp2 cy = {{{0x3e2f585da55c9ad1ULL, 0x4294213d86c18183ULL, 0x382844c88b623732ULL, 0x92ad2afd19103e18ULL,
+                           0x1d794e4fac7cf0b9ULL, 0x0bd592fc7d825ec8ULL}},
+                         {{0x7bcfa7a25aa30fdaULL, 0xdc17dec12a927e7cULL, 0x2f088dd86b4ebef1ULL, 0xd1ca2087da74d4a7ULL,
+                           0x2da2596696cebc1dULL, 0x0e2b7eedbbfd87d2ULL}}};
+  return G2Projective{fp2_mul(fp2_frobenius_map(s.x), cx), fp2_mul(fp2_frobenius_map(s.y), cy), fp2_frobenius_map(s.z)};
+}
+// src/g2.rs:537-554
+static inline bool g2p_eq(const G2Projective &a, const G2Projective &b) {
+  Fp2 x1 = fp2_mul(a.x, b.z), x2 = fp2_mul(b.x, a.z), y1 = fp2_mul(a.y, b.z), y2 = fp2_mul(b.y, a.z);
+  bool az = fp2_is_zero(a.z), bz = fp2_is_zero(b.z);
+  return (az && bz) || (!az && !bz && fp2_eq(x1, x2) && fp2_eq(y1, y2));
+}
+// src/g2.rs:475-482 : psi(P) == [x]P
+static inline bool g2a_is_torsion_free(const G2Affine &p) {
+  G2Projective pp = g2p_from_affine(p);
+  return g2p_eq(g2p_psi(pp), g2p_mul_by_x(pp));
 }
 static inline bool g2a_is_on_curve(const G2Affine &p) {  // src/g2.rs:487-491
   return p.infinity || fp2_eq(fp2_sub(fp2_square(p.y), fp2_mul(fp2_square(p.x), p.x)), G2_B);

@@ -453,6 +453,20 @@ int orc_g2_from_uncompressed(const uint8_t *in, uint64_t *xy, uint8_t *inf) {
   return ok;
 }
 
+// is_torsion_free / is_on_curve per point (src/g1.rs:401-418, src/g2.rs:475-491): out[i] bit0 on curve, bit1 torsion free
+void orc_g1_checks(const uint64_t *xy, const uint8_t *inf, size_t n, uint8_t *out) {
+  for (size_t i = 0; i < n; i++) {
+    G1Affine p = load_g1a(xy, inf, i);
+    out[i] = (g1a_is_on_curve(p) ? 1 : 0) | (g1a_is_torsion_free(p) ? 2 : 0);
+  }
+}
+void orc_g2_checks(const uint64_t *xy, const uint8_t *inf, size_t n, uint8_t *out) {
+  for (size_t i = 0; i < n; i++) {
+    G2Affine p = load_g2a(xy, inf, i);
+    out[i] = (g2a_is_on_curve(p) ? 1 : 0) | (g2a_is_torsion_free(p) ? 2 : 0);
+  }
+}
+
 // ---------------------------------------------------------------- pairings
 // out[i] = MillerLoopResult of (p_i, q_i), unprepared, identity handling as pairing() :636-651
 void orc_miller_loop(const uint64_t *pxy, const uint8_t *pinf, const uint64_t *qxy, const uint8_t *qinf, size_t n,

@@ -219,6 +219,14 @@ class _Group:
         self._f("msm_pippenger")(_p(xy), _p(inf), _p(s), C.c_size_t(xy.shape[0]), _p(out), c, threads)
         return out
 
+    def checks(self, xy, inf=None):
+        """per point: bit 0 = is_on_curve, bit 1 = is_torsion_free"""
+        xy = _u64(xy, self.aw)
+        inf = None if inf is None else _u8(inf)
+        out = np.empty(xy.shape[0], np.uint8)
+        self._f("checks")(_p(xy), _p(inf), C.c_size_t(xy.shape[0]), _p(out))
+        return out
+
     def to_compressed(self, xy, inf=0):
         out = np.empty(48 * self.k, np.uint8)
         self._f("to_compressed")(_p(_u64(xy, self.aw)), int(inf), _p(out))

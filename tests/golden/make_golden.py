@@ -41,8 +41,8 @@ KATS = {
                    "test_sqrt", "test_inversion", "test_lexicographic_largest"]),
     "fp6.rs": (6, ["test_arithmetic"]),
     "fp12.rs": (6, ["test_arithmetic"]),
-    "g1.rs": (6, ["test_doubling", "test_projective_addition", "test_mixed_addition", "test_beta"]),
-    "g2.rs": (6, ["test_doubling", "test_projective_addition", "test_mixed_addition"]),
+    "g1.rs": (6, ["test_doubling", "test_projective_addition", "test_mixed_addition", "test_beta", "test_is_torsion_free"]),
+    "g2.rs": (6, ["test_doubling", "test_projective_addition", "test_mixed_addition", "test_is_torsion_free"]),
     "pairings.rs": (6, ["generator"]),           # Gt::generator(), src/pairings.rs:359-475
     "scalar.rs": (4, ["test_from_bytes_wide_maximum"]),
     "tests/mod.rs": (6, ["test_pairing_result_against_relic"]),   # expected Gt, Montgomery limbs (:114-231)

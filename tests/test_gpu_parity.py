@@ -333,3 +333,49 @@ def test_g1_msm_with_and_without_glv(eng, orc, glv):
         _msm_case(eng, orc, 1, xy[:3], inf[:3], s[:3], cs=(0, 4))
     finally:
         eng.set_tuning("g1_glv", 0)
+
+
+@pytest.mark.parametrize("k", [1, 2])
+def test_subgroup_checks(eng, orc, k):
+    """is_on_curve / is_torsion_free on the device vs the oracle, including the reference's KAT of a curve point
+    outside the q-order subgroup (src/g1.rs:1598-1623, src/g2.rs:1862-1907)"""
+    kat = json.load(open(os.path.join(GOLD, "kat.json")))
+    key = "g%d.rs::test_is_torsion_free" % k
+    bad = np.concatenate([np.array([int(x, 16) for x in g], dtype=np.uint64) for g in kat[key][:2 * k]])
+    G = orc.G1 if k == 1 else orc.G2
+    rng = np.random.default_rng(1300 + k)
+    _, xy, inf = util.rand_points(orc, k, rng, 20)
+    xy = np.concatenate([xy, bad[None, :]])
+    inf = np.concatenate([inf, [0]]).astype(np.uint8)
+    inf[3] = 1
+    xy[5, -1] ^= 1                                   # off the curve
+    got = eng.check(k, xy, inf)
+    exp = G.checks(xy, inf)
+    assert np.array_equal(got, exp)
+    assert got[-1] == 1 and got[0] == 3 and got[3] == 3 and (got[5] & 1) == 0
+
+
+def test_g2_prepared(eng, orc):
+    """G2Prepared coefficients limb-exact vs the oracle (src/pairings.rs:504-546, 68 triples :539), and
+    multi_miller_loop over prepared terms, identities skipped (:554-603)"""
+    rng = np.random.default_rng(1400)
+    n = 7
+    _, pxy, pinf = util.rand_points(orc, 1, rng, n)
+    _, qxy, qinf = util.rand_points(orc, 2, rng, n)
+    qinf[2] = 1
+    pinf[4] = 1
+    co = eng.g2_prepare(qxy, qinf)
+    for i in range(n):
+        assert eq(co[i], orc.g2_prepare(qxy[i], qinf[i])), i
+    mm = eng.multi_miller_loop_prepared(pxy, pinf, co, qinf)
+    assert eq(mm, orc.multi_miller_loop(pxy, pinf, qxy, qinf))
+    assert eq(mm, eng.multi_miller_loop(pxy, pinf, qxy, qinf))          # == the unprepared product mode
+    import torch
+    dev = torch.device("cuda", eng.device)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int64) if a.dtype == np.uint64 else a).to(dev)
+    dco = torch.empty((n, 68 * 36), dtype=torch.int64, device=dev)
+    eng.g2_prepare_dev(t(qxy), t(qinf), n, dco)
+    assert eq(dco.cpu().numpy().view(np.uint64), co)
+    ml = torch.empty((n, 72), dtype=torch.int64, device=dev)
+    eng.miller_loop_prepared_batch_dev(t(pxy), t(pinf), dco, t(qinf), n, ml)
+    assert eq(ml.cpu().numpy().view(np.uint64), orc.miller_loop(pxy, pinf, qxy, qinf, threads=4))

@@ -324,3 +324,26 @@ def test_msm_pippenger_matches_naive(orc):
         for c in (4, 7):
             b = G.to_affine(G.msm_pippenger(xy, inf, s, c=c, threads=4))
             assert eq(a[0], b[0]) and a[1][0] == b[1][0]
+
+
+# ----------------------------------------------------------------------------- subgroup checks (src/g1.rs:1598-1623, src/g2.rs:1862-1907)
+def test_is_torsion_free_kats(orc):
+    k = "g1.rs::test_is_torsion_free"               # a curve point outside the q-order subgroup
+    a = cat(k, [0, 1])
+    assert orc.G1.checks(a)[0] == 1                  # on the curve, NOT torsion free
+    gxy, ginf = orc.G1.to_affine(orc.G1.generator())
+    ixy, iinf = orc.G1.affine_identity()
+    assert orc.G1.checks(gxy, ginf)[0] == 3 and orc.G1.checks(ixy, iinf)[0] == 3
+    k = "g2.rs::test_is_torsion_free"
+    a = cat(k, [0, 1, 2, 3])
+    assert orc.G2.checks(a)[0] == 1
+    hxy, hinf = orc.G2.to_affine(orc.G2.generator())
+    ixy, iinf = orc.G2.affine_identity()
+    assert orc.G2.checks(hxy, hinf)[0] == 3 and orc.G2.checks(ixy, iinf)[0] == 3
+    # every golden [i]G is in the subgroup
+    rng = np.random.default_rng(2)
+    t = rng.integers(0, 256, (6, 32), dtype=np.uint8)
+    t[:, 31] &= 0x3f
+    for G in (orc.G1, orc.G2):
+        xy, inf = G.batch_normalize(G.mul(np.repeat(G.generator(), 6, 0), t))
+        assert (G.checks(xy, inf) == 3).all()
