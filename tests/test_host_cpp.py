@@ -1,0 +1,50 @@
+"""The C++ host mirror (bls12_381_b200/host/bls12_381.hpp) compiles against the C ABI, links with the shared
+library, and keeps the reference's error behaviour: no GPU -> Engine construction throws (no CPU fallback);
+batch_normalize keeps the reference's length assertion (src/g1.rs:807).  CPU only."""
+import os
+import subprocess
+import tempfile
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = r'''
+#include <cstdio>
+#include "bls12_381_b200/host/bls12_381.hpp"
+using namespace bls12_381;
+int main() {
+  static_assert(sizeof(G1Affine) == 97 || sizeof(G1Affine) == 104, "G1Affine = coords + flag");
+  try {
+    Engine e(0);
+    std::vector<G1Projective> p(2);
+    std::vector<G1Affine> q(3);
+    try {
+      G1Projective::batch_normalize(e, p, q);      // lengths differ: must throw like assert_eq! in the reference
+      std::puts("NO-THROW");
+      return 2;
+    } catch (const Error &err) {
+      std::printf("GPU-PRESENT length-assert code=%d\n", err.code);
+      return 0;
+    }
+  } catch (const Error &err) {
+    std::printf("NO-GPU code=%d what=%s\n", err.code, err.what());
+    return err.code == B200_ENODEV ? 0 : 3;
+  }
+}
+'''
+
+
+def test_cpp_host_mirror_compiles_links_and_fails_loudly_without_gpu():
+    from bls12_381_b200 import _lib
+    _lib.load()                                   # makes sure the .so exists
+    so_dir = os.path.join(ROOT, "bls12_381_b200")
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "t.cpp")
+        exe = os.path.join(d, "t")
+        open(src, "w").write(SRC)
+        cmd = ["g++", "-std=c++17", "-I", ROOT, src, "-o", exe, "-L", so_dir, "-lbls12381_b200", "-Wl,-rpath," + so_dir]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, (r.stdout, r.stderr)
+        assert "NO-GPU code=-2" in r.stdout or "GPU-PRESENT" in r.stdout
