@@ -145,6 +145,11 @@ __global__ void __launch_bounds__(256) k_msm_scatter(msm_plan pl, const uint32_t
 // a warp walk buckets of (nearly) equal length (round-1 ncu: 23/32 active lanes with natural order) and
 // the last, partially filled wave holds only the short buckets.  Counting sort on min(count, 1023).
 constexpr int SIZE_BINS = 1024;
+// Buckets with >= GIANT_BUCKET points (skewed or adversarial scalars: e.g. all-equal scalars put all n points of a
+// window into ONE bucket) would serialise on one thread.  They land in the last size bin, i.e. at the FRONT of
+// `order`; each is split into GIANT_PARTS ranges summed by whole blocks and then combined.
+constexpr uint32_t GIANT_BUCKET = SIZE_BINS - 1;
+constexpr int GIANT_PARTS = 32;
 __global__ void __launch_bounds__(256) k_msm_size_hist(size_t total, const uint32_t *hist, uint32_t *size_hist) {
   __shared__ uint32_t sh[SIZE_BINS];
   for (int i = threadIdx.x; i < SIZE_BINS; i += blockDim.x) sh[i] = 0;
@@ -199,6 +204,7 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(int nbuckets, size
   size_t j = k / nbuckets;
   const uint32_t *idx = sorted + j * sstride + offsets[k];
   uint32_t cnt = hist[k];
+  if (cnt >= GIANT_BUCKET) return;  // split across blocks by k_msm_giant_parts / k_msm_giant_final
   xyzz<F> acc = xyzz_identity<F>();
   if constexpr (PREFETCH) {
     // software pipeline: the NEXT point of the bucket is copied global -> shared with cp.async (LDGSTS, no
@@ -302,6 +308,7 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accumulate_g2sm(int nbuckets,
   size_t j = k / nbuckets;
   const uint32_t *idx = sorted + j * sstride + offsets[k];
   uint32_t cnt = hist[k];
+  if (cnt >= GIANT_BUCKET) return;  // handled by k_msm_giant_parts / k_msm_giant_final
   const sm_fp2 X{sm + threadIdx.x}, Y{sm + 24 * 128 + threadIdx.x}, ZZ{sm + 48 * 128 + threadIdx.x},
       ZZZ{sm + 72 * 128 + threadIdx.x};
   bool empty = true;
@@ -340,6 +347,60 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accumulate_g2sm(int nbuckets,
     out = proj<fp2>{M2(X.get(), zzz), M2(Y.get(), zz), M2(zz, zzz)};
   }
   proj_store<fp2>(buckets + (size_t)288 * k, out);
+}
+
+// block (b) works on giant g = b / GIANT_PARTS, part b % GIANT_PARTS; grid-stride over (giant, part) pairs.
+// n_giant is read from the size histogram on the device (no host round trip); usually 0 -> immediate exit.
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_giant_parts(int nbuckets, size_t slot0, const uint32_t *size_hist,
+                                                       const uint32_t *order, const char *points, const char *bx,
+                                                       size_t sstride, const uint32_t *offsets, const uint32_t *hist,
+                                                       const uint32_t *sorted, char *gparts, uint32_t max_giants) {
+  extern __shared__ char smem[];
+  constexpr size_t FB = field_traits<F>::bytes, AB = 2 * FB, PB = 3 * FB;
+  uint32_t ng = min(size_hist[SIZE_BINS - 1], max_giants);
+  for (uint32_t item = blockIdx.x; item < ng * GIANT_PARTS; item += gridDim.x) {
+    uint32_t g = item / GIANT_PARTS, part = item % GIANT_PARTS;
+    size_t k = slot0 + order[g];
+    size_t j = k / nbuckets;
+    const uint32_t *idx = sorted + j * sstride + offsets[k];
+    uint32_t cnt = hist[k];
+    uint32_t per = (cnt + GIANT_PARTS - 1) / GIANT_PARTS;
+    uint32_t lo = part * per, hi = min(lo + per, cnt);
+    xyzz<F> acc = xyzz_identity<F>();
+    for (uint32_t t = lo + threadIdx.x; t < hi; t += blockDim.x) {
+      uint32_t e = __ldg(idx + t);
+      const char *pp = points + AB * (size_t)(e & ENT_IDX);
+      F x = field_traits<F>::load_ro((e & ENT_PHI) ? bx + FB * (size_t)(e & ENT_IDX) : pp), y = field_traits<F>::load_ro(pp + FB);
+      if (e >> 31) y = f_neg(y);
+      acc = xyzz_add_mixed(acc, x, y);
+    }
+    proj_store<F>(smem + PB * threadIdx.x, xyzz_to_proj(acc));
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+      if ((int)threadIdx.x < s) {
+        proj<F> a = proj_load<F>(smem + PB * threadIdx.x), b2 = proj_load<F>(smem + PB * (threadIdx.x + s));
+        proj_store<F>(smem + PB * threadIdx.x, proj_add(a, b2));
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) proj_store<F>(gparts + PB * item, proj_load<F>(smem));
+    __syncthreads();
+  }
+}
+// one warp per giant: sum its GIANT_PARTS partial sums (lane-parallel complete additions), write the bucket
+template <class F>
+__global__ void __launch_bounds__(32) k_msm_giant_final(size_t slot0, const uint32_t *size_hist, const uint32_t *order,
+                                                      const char *gparts, char *buckets, uint32_t max_giants) {
+  constexpr size_t PB = 3 * field_traits<F>::bytes;
+  uint32_t ng = min(size_hist[SIZE_BINS - 1], max_giants);
+  const int lane = threadIdx.x;
+  for (uint32_t g = blockIdx.x; g < ng; g += gridDim.x) {
+    proj<F> acc = proj_identity<F>();
+#pragma unroll 1
+    for (int p = 0; p < GIANT_PARTS; p++) acc = warp_add(acc, proj_load<F>(gparts + PB * ((size_t)g * GIANT_PARTS + p)), lane);
+    if (lane == 0) proj_store<F>(buckets + PB * (slot0 + order[g]), acc);
+  }
 }
 
 // GLV prologue: bx[i] = beta * x_i  (x-coordinate of phi(P_i))
@@ -481,9 +542,11 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
   int chunk = (pl.nbuckets + chunks - 1) / chunks;
   if (chunk < 1) chunk = 1;
   int blocks_per_window = chunks / RB;
+  // at most (entries of the largest group) / GIANT_BUCKET giants can exist at once
+  const uint32_t max_giants = (uint32_t)((size_t)pl.nloc * sstride / GIANT_BUCKET + pl.nloc);
   size_t need = 4 * arena_pad(total * 4) + 3 * arena_pad(4 * SIZE_BINS * 4) + arena_pad((size_t)pl.nloc * sstride * 4) +
                 arena_pad(total * PB) + arena_pad((size_t)pl.nloc * blocks_per_window * PB) + arena_pad(PB) +
-                (pl.glv ? arena_pad(48 * n) : 0) + 4096;
+                (pl.glv ? arena_pad(48 * n) : 0) + arena_pad((size_t)max_giants * GIANT_PARTS * PB) + 4096;
   int rc = arena_reserve(ctx, need);
   if (rc != B200_OK) return rc;
   uint32_t *hist = arena_take<uint32_t>(ctx, total);
@@ -497,6 +560,7 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
   char *partials = arena_take<char>(ctx, (size_t)pl.nloc * blocks_per_window * PB);
   char *hacc = arena_take<char>(ctx, PB);
   char *bx = pl.glv ? arena_take<char>(ctx, 48 * n) : nullptr;
+  char *gparts = arena_take<char>(ctx, (size_t)max_giants * GIANT_PARTS * PB);
   if (pl.glv) B200_LAUNCH(ctx, k_msm_glv_bx, nblk(n, 256), 256, 0, (const char *)points, n, bx);
   // hist and cursor are adjacent: one memset
   B200_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)((char *)offsets - (char *)hist), ctx->stream));
@@ -571,6 +635,10 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
       B200_LAUNCH(ctx, (k_msm_accumulate_g2sm<2>), nblk(gtotal, 128), 128, 96 * 128 * 4, pl.nbuckets, gtotal, s0,
                   (const char *)points, sstride, offsets, hist, sorted, order + s0, buckets);
     }
+    // giant buckets of this group (normally none: both kernels read the count on the device and exit at once)
+    B200_LAUNCH(ctx, k_msm_giant_parts<F>, 4 * ctx->sm_count, 128, 128 * PB, pl.nbuckets, s0, sh, order + s0, (const char *)points,
+                (const char *)bx, sstride, offsets, hist, sorted, gparts, max_giants);
+    B200_LAUNCH(ctx, k_msm_giant_final<F>, 64, 32, 0, s0, sh, order + s0, gparts, buckets, max_giants);
     B200_CUDA(ctx, cudaEventRecord(ctx->ev_sync[1 + 2 * g], ctx->stream));
     if (g + 1 < ng) {  // sort the next group under this group's accumulate
       int rc1 = sort_group(ctx->stream2, j_lo - gsz[g + 1], gsz[g + 1]);

@@ -379,3 +379,28 @@ def test_g2_prepared(eng, orc):
     ml = torch.empty((n, 72), dtype=torch.int64, device=dev)
     eng.miller_loop_prepared_batch_dev(t(pxy), t(pinf), dco, t(qinf), n, ml)
     assert eq(ml.cpu().numpy().view(np.uint64), orc.miller_loop(pxy, pinf, qxy, qinf, threads=4))
+
+
+@pytest.mark.parametrize("k,n", [(1, 40000), (2, 12000)])
+def test_msm_giant_buckets(eng, orc, k, n):
+    """skewed scalars: all-equal scalars put every point of a window into ONE bucket (>= 1023 points -> split across
+    blocks by k_msm_giant_parts); half-equal/half-random mixes giant and ordinary buckets"""
+    import time
+    rng = np.random.default_rng(1500 + k)
+    base = util.rand_points(orc, k, rng, 64)
+    reps = (n + 63) // 64
+    xy = np.tile(base[1], (reps, 1))[:n].copy()
+    inf = np.tile(base[2], reps)[:n].copy()
+    same = util.rand_scalars(rng, 1)
+    s = np.repeat(same, n, 0)
+    G = orc.G1 if k == 1 else orc.G2
+    for variant in range(2):
+        if variant == 1:
+            s[n // 2:] = rng.integers(0, 256, (n - n // 2, 32), dtype=np.uint8)
+            s[n // 2:, 31] &= 0x3f
+        t0 = time.perf_counter()
+        got = G.to_affine(eng.msm(k, xy, inf, s))
+        dt = time.perf_counter() - t0
+        exp = G.to_affine(G.msm_pippenger(xy, inf, s, c=12, threads=16))
+        assert eq(got[0], exp[0]) and got[1][0] == exp[1][0], (k, variant)
+        assert dt < 2.0, "giant buckets must not serialise on one thread (took %.2f s)" % dt
