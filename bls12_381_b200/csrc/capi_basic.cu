@@ -367,9 +367,6 @@ int b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int value) {
   } else if (!strcmp(key, "pairing_chunks")) {
     if (value < 1 || value > 64) return B200_EINVAL;
     ctx->tune_pairing_chunks = value;
-  } else if (!strcmp(key, "pairing_blocks")) {
-    if (value != 4 && value != 8) return B200_EINVAL;
-    ctx->tune_pairing_blocks = value;
   } else {
     return B200_EINVAL;
   }

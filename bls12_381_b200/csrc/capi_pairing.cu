@@ -13,19 +13,19 @@ using namespace b200;
   int b200_pair_g2_prepare_##v(b200_ctx *, cudaStream_t, const void *, const void *, size_t, void *);                  \
   int b200_pair_miller_prepared_##v(b200_ctx *, cudaStream_t, const void *, const void *, const void *, const void *,  \
                                     size_t, void *);
-DECL_VARIANT(v4) DECL_VARIANT(v8)
+DECL_VARIANT(v4)
 
 namespace {
 
-// register-budget variants of the pairing kernels (pairing_v*.cu); ctx->tune_pairing_blocks selects one
+// The pairing kernels live in their own translation unit (pairing_v4.cu: 255 registers, 4 resident 64-thread blocks
+// per SM, Fp2 multiply = Karatsuba over fp_mul_c calls).  Lower register budgets (168 / 128) and the inlined /
+// lazily reduced Fp2 multiplies were built the same way, measured slower, and removed.
 int miller_on(b200_ctx *ctx, cudaStream_t st, const void *p, const void *pi, const void *q, const void *qi, size_t n,
               void *out) {
-  return ctx->tune_pairing_blocks == 8 ? b200_pair_miller_v8(ctx, st, p, pi, q, qi, n, out)
-                                       : b200_pair_miller_v4(ctx, st, p, pi, q, qi, n, out);
+  return b200_pair_miller_v4(ctx, st, p, pi, q, qi, n, out);
 }
 int final_exp_on(b200_ctx *ctx, cudaStream_t st, const void *in, size_t n, void *out) {
-  return ctx->tune_pairing_blocks == 8 ? b200_pair_final_exp_v8(ctx, st, in, n, out)
-                                       : b200_pair_final_exp_v4(ctx, st, in, n, out);
+  return b200_pair_final_exp_v4(ctx, st, in, n, out);
 }
 int miller_dev(b200_ctx *ctx, const void *p, const void *pi, const void *q, const void *qi, size_t n, void *out) {
   return miller_on(ctx, ctx->stream, p, pi, q, qi, n, out);

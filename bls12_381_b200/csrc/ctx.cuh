@@ -21,7 +21,6 @@ struct b200_ctx {
   char err[256] = {0};
   uint64_t launches = 0;
   int msm_c = 0;
-  int tune_pairing_blocks = 4; // resident 64-thread blocks/SM the pairing kernels are compiled for (4: 255 regs, measured best; 8: 128 regs, spills)
   // G1 MSM: GLV split k = k1 + k2*lambda (8 windows of 2n entries instead of 16 of n).  0 off (default), 1 on,
   // 2 = on for window-sharded calls only.  Implemented, parity-tested, and measured NEGATIVE at 2^20 on B200:
   // 1 GPU 9.34 vs 9.02 ms, 8 GPUs 3.66 vs 3.19 ms — halving the windows halves the (window x bucket) slots, i.e. the

@@ -70,7 +70,7 @@ uint64_t b200_ctx_launch_count(const b200_ctx *ctx);
 int b200_ctx_set_timing(b200_ctx *ctx, int on);
 int b200_ctx_get_timing(b200_ctx *ctx, char *names, size_t names_len, float *ms, int max);
 /* tuning knobs by name: "msm_window" (0 = auto, else 2..24), "g1_glv" (0 off, 1 on, 2 auto = on for window-sharded calls), "g1_prefetch" (0|1), "g2_acc_blocks" (G2 bucket kernel variant: 2 registers,
- * 3 shared-memory accumulator built for 3 blocks/SM, 4 shared-memory accumulator at 2 blocks/SM = default), "pairing_blocks" (4|8), "pairing_chunks" (1..64 independent chunks of a
+ * 3 shared-memory accumulator built for 3 blocks/SM, 4 shared-memory accumulator at 2 blocks/SM = default), "pairing_chunks" (1..64 independent chunks of a
  * pairing batch in flight).  Unknown key or bad value -> B200_EINVAL. */
 int b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int value);
 /* MSM tuning: window bits c (0 = automatic from n); returns previous value */
