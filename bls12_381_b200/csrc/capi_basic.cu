@@ -6,6 +6,7 @@
 #include "ctx.cuh"
 #include "curve.cuh"
 #include "curve_warp.cuh"
+#include "fp_inv.cuh"
 #include "pairing.cuh"
 
 using namespace b200;
@@ -14,7 +15,7 @@ using namespace b200;
 namespace {
 
 template <int LEVEL>
-__global__ void k_tower_op(int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n) {
+__global__ void k_tower_op(int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n, const uint32_t *pow2) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   constexpr int W = 6 * LEVEL;
@@ -28,6 +29,7 @@ __global__ void k_tower_op(int op, const uint64_t *a, const uint64_t *b, uint64_
       case B200_OP_SUB: r = fp_sub(x, y); break;
       case B200_OP_SQUARE: r = fp_sqr(x); break;
       case B200_OP_NEG: r = fp_neg(x); break;
+      case B200_OP_INVERT_FAST: r = fp_inv_fast(x, pow2); break;
       default: r = fp_inv(x); break;
     }
     fp_store(po, r);
@@ -137,8 +139,14 @@ __global__ void __launch_bounds__(128) k_mul_batch_warp(const char *p, const uin
 // batch_normalize (src/g1.rs:806-839): Montgomery's trick per thread over a strided subsequence
 // i = t, t+T, t+2T, ... (coalesced across the warp).  One inversion per thread.  The prefix products
 // are parked in out.x exactly like the reference parks them in q.x.
+B200_DEV fp f_inv_gcd(const fp &a, const uint32_t *pow2) { return fp_inv_fast(a, pow2); }
+B200_DEV fp2 f_inv_gcd(const fp2 &a, const uint32_t *pow2) {  // src/fp2.rs:300-320 over the binary-GCD Fp inverse
+  fp t = fp_inv_fast(fp_add(fp_mul_c(a.c0, a.c0), fp_mul_c(a.c1, a.c1)), pow2);
+  return fp2{fp_mul_c(a.c0, t), fp_mul_c(a.c1, fp_neg(t))};
+}
 template <class F>
-__global__ void __launch_bounds__(128) k_batch_normalize(const char *p, size_t n, char *oxy, uint8_t *oinf) {
+__global__ void __launch_bounds__(128) k_batch_normalize(const char *p, size_t n, char *oxy, uint8_t *oinf,
+                                                       const uint32_t *pow2) {
   size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x, T = (size_t)gridDim.x * blockDim.x;
   if (t >= n) return;
   constexpr size_t FB = field_traits<F>::bytes, PB = 3 * FB, AB = 2 * FB;
@@ -148,7 +156,7 @@ __global__ void __launch_bounds__(128) k_batch_normalize(const char *p, size_t n
     F z = field_traits<F>::load(p + PB * i + 2 * FB);
     if (!f_is_zero(z)) acc = f_mul(acc, z);
   }
-  acc = f_inv(acc);
+  acc = f_inv_gcd(acc, pow2);  // one inversion per thread: binary GCD (fp_inv.cuh), same value as the Fermat inverse
   size_t last = t + ((n - 1 - t) / T) * T;
   for (size_t i = last;; i -= T) {
     F z = field_traits<F>::load(p + PB * i + 2 * FB);
@@ -222,7 +230,7 @@ int batch_normalize_dev(b200_ctx *ctx, const void *p, size_t n, void *oxy, void 
   size_t threads = (n + 63) / 64;
   unsigned block = 128;
   unsigned grid = nblk(threads, block);
-  B200_LAUNCH(ctx, k_batch_normalize<F>, grid, block, 0, (const char *)p, n, (char *)oxy, (uint8_t *)oinf);
+  B200_LAUNCH(ctx, k_batch_normalize<F>, grid, block, 0, (const char *)p, n, (char *)oxy, (uint8_t *)oinf, ctx->inv_pow2);
   return B200_OK;
 }
 template <class F>
@@ -299,6 +307,17 @@ int b200_ctx_create(int device, b200_ctx **out) {
   }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+  if (cudaMalloc((void **)&c->inv_pow2, FP_INV_TABLE_WORDS * sizeof(uint32_t)) != cudaSuccess) {
+    b200_ctx_destroy(c);
+    cudaSetDevice(prev);
+    return B200_ENOMEM;
+  }
+  k_fp_inv_table_init<<<1, 32, 0, c->stream>>>(c->inv_pow2);
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
+    b200_ctx_destroy(c);
+    cudaSetDevice(prev);
+    return B200_ECUDA;
+  }
   cudaSetDevice(prev);
   *out = c;
   return B200_OK;
@@ -322,6 +341,7 @@ void b200_ctx_destroy(b200_ctx *ctx) {
   }
   for (int i = 0; i < b200_ctx::N_SYNC_EVENTS; i++)
     if (ctx->ev_sync[i]) cudaEventDestroy(ctx->ev_sync[i]);
+  if (ctx->inv_pow2) cudaFree(ctx->inv_pow2);
   if (ctx->arena) cudaFree(ctx->arena);
   if (ctx->stage) cudaFree(ctx->stage);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -359,6 +379,9 @@ int b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int value) {
   } else if (!strcmp(key, "g2_acc_blocks")) {
     if (value < 2 || value > 4) return B200_EINVAL;  // 2: registers; 3: shared memory, 3 blocks/SM; 4: shared, 2 blocks
     ctx->tune_g2_acc_blocks = value;
+  } else if (!strcmp(key, "msm_affine_levels")) {
+    if (value < -1 || value > 3) return B200_EINVAL;
+    ctx->tune_msm_affine_levels = value;
   } else if (!strcmp(key, "g1_glv")) {
     if (value < 0 || value > 2) return B200_EINVAL;
     ctx->tune_g1_glv = value;
@@ -410,10 +433,10 @@ int b200_tower_op(b200_ctx *ctx, int level, int op, const uint64_t *a, const uin
   if (level != 1 && level != 2 && level != 6 && level != 12) return B200_EINVAL;
   bool binary = op == B200_OP_MUL || op == B200_OP_ADD || op == B200_OP_SUB;
   if (binary && !b) return B200_EINVAL;
-  static const int ok1[] = {0, 1, 2, 3, 4, 5}, ok2[] = {0, 1, 2, 3, 4, 5, 6, 7, 8}, ok6[] = {0, 1, 2, 3, 4, 5, 6, 8},
+  static const int ok1[] = {0, 1, 2, 3, 4, 5, 10}, ok2[] = {0, 1, 2, 3, 4, 5, 6, 7, 8}, ok6[] = {0, 1, 2, 3, 4, 5, 6, 8},
                    ok12[] = {0, 3, 5, 6, 7, 9};
   const int *okl = level == 1 ? ok1 : level == 2 ? ok2 : level == 6 ? ok6 : ok12;
-  int nok = level == 1 ? 6 : level == 2 ? 9 : level == 6 ? 8 : 6;
+  int nok = level == 1 ? 7 : level == 2 ? 9 : level == 6 ? 8 : 6;
   bool found = false;
   for (int i = 0; i < nok; i++) found |= okl[i] == op;
   if (!found) return B200_EINVAL;
@@ -425,10 +448,10 @@ int b200_tower_op(b200_ctx *ctx, int level, int op, const uint64_t *a, const uin
   if (st.rc != B200_OK) return st.rc;
   unsigned block = level >= 6 ? 64 : 128;
   switch (level) {
-    case 1: B200_LAUNCH(ctx, k_tower_op<1>, nblk(n, block), block, 0, op, da, db, dout, n); break;
-    case 2: B200_LAUNCH(ctx, k_tower_op<2>, nblk(n, block), block, 0, op, da, db, dout, n); break;
-    case 6: B200_LAUNCH(ctx, k_tower_op<6>, nblk(n, block), block, 0, op, da, db, dout, n); break;
-    default: B200_LAUNCH(ctx, k_tower_op<12>, nblk(n, block), block, 0, op, da, db, dout, n); break;
+    case 1: B200_LAUNCH(ctx, k_tower_op<1>, nblk(n, block), block, 0, op, da, db, dout, n, ctx->inv_pow2); break;
+    case 2: B200_LAUNCH(ctx, k_tower_op<2>, nblk(n, block), block, 0, op, da, db, dout, n, ctx->inv_pow2); break;
+    case 6: B200_LAUNCH(ctx, k_tower_op<6>, nblk(n, block), block, 0, op, da, db, dout, n, ctx->inv_pow2); break;
+    default: B200_LAUNCH(ctx, k_tower_op<12>, nblk(n, block), block, 0, op, da, db, dout, n, ctx->inv_pow2); break;
   }
   st.back(out, dout, bytes);
   return st.sync();

@@ -23,6 +23,7 @@
 #include "curve.cuh"
 #include "curve_warp.cuh"
 #include "glv.cuh"
+#include "msm_affine.cuh"
 
 using namespace b200;
 
@@ -150,12 +151,18 @@ constexpr int SIZE_BINS = 1024;
 // `order`; each is split into GIANT_PARTS ranges summed by whole blocks and then combined.
 constexpr uint32_t GIANT_BUCKET = SIZE_BINS - 1;
 constexpr int GIANT_PARTS = 32;
-__global__ void __launch_bounds__(256) k_msm_size_hist(size_t total, const uint32_t *hist, uint32_t *size_hist) {
+// scheduling key of a slot: giants (by their level-0 population) in the last bin, everything else by the number
+// of entries the bucket kernel will walk (after the affine levels, if any)
+__device__ __forceinline__ uint32_t size_key(const uint32_t *counts, const uint32_t *hist0, size_t k) {
+  return hist0[k] >= (uint32_t)SIZE_BINS - 1 ? (uint32_t)SIZE_BINS - 1 : min(counts[k], (uint32_t)SIZE_BINS - 2);
+}
+__global__ void __launch_bounds__(256) k_msm_size_hist(size_t total, const uint32_t *counts, const uint32_t *hist0,
+                                                     uint32_t *size_hist) {
   __shared__ uint32_t sh[SIZE_BINS];
   for (int i = threadIdx.x; i < SIZE_BINS; i += blockDim.x) sh[i] = 0;
   __syncthreads();
   size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (k < total) atomicAdd(&sh[min(hist[k], (uint32_t)SIZE_BINS - 1)], 1u);
+  if (k < total) atomicAdd(&sh[size_key(counts, hist0, k)], 1u);
   __syncthreads();
   for (int i = threadIdx.x; i < SIZE_BINS; i += blockDim.x)
     if (sh[i]) atomicAdd(&size_hist[i], sh[i]);
@@ -176,11 +183,11 @@ __global__ void __launch_bounds__(SIZE_BINS) k_msm_size_scan(const uint32_t *siz
   size_base[r] = part[threadIdx.x] - v;
 }
 // warp-aggregated scatter: lanes that hit the same bin are found with match.any, one atomic per group
-__global__ void __launch_bounds__(256) k_msm_size_scatter(size_t total, const uint32_t *hist, const uint32_t *size_base,
-                                                        uint32_t *size_cursor, uint32_t *order) {
+__global__ void __launch_bounds__(256) k_msm_size_scatter(size_t total, const uint32_t *counts, const uint32_t *hist0,
+                                                        const uint32_t *size_base, uint32_t *size_cursor, uint32_t *order) {
   size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (k >= total) return;
-  uint32_t bin = min(hist[k], (uint32_t)SIZE_BINS - 1);
+  uint32_t bin = size_key(counts, hist0, k);
   unsigned lane = threadIdx.x & 31u;
   unsigned peers = __match_any_sync(__activemask(), bin);
   int leader = __ffs(peers) - 1;
@@ -547,6 +554,10 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
   size_t need = 4 * arena_pad(total * 4) + 3 * arena_pad(4 * SIZE_BINS * 4) + arena_pad((size_t)pl.nloc * sstride * 4) +
                 arena_pad(total * PB) + arena_pad((size_t)pl.nloc * blocks_per_window * PB) + arena_pad(PB) +
                 (pl.glv ? arena_pad(48 * n) : 0) + arena_pad((size_t)max_giants * GIANT_PARTS * PB) + 4096;
+  if (ctx->tune_msm_affine_levels != 0) {  // upper bound of the affine-level scratch (largest group <= all local windows)
+    need += 8 * arena_pad(total * 4) + 3 * 256;
+    for (int l = 1; l <= 3; l++) need += arena_pad((size_t)pl.nloc * ((sstride >> l) + pl.nbuckets + 8) * 2 * field_traits<F>::bytes);
+  }
   int rc = arena_reserve(ctx, need);
   if (rc != B200_OK) return rc;
   uint32_t *hist = arena_take<uint32_t>(ctx, total);
@@ -568,8 +579,20 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
   // Three streams: accumulate(g) on `stream`; reduce(g) on stream2 (after accumulate(g)); horner(g) on
   // stream3 (after reduce(g) and horner(g-1)).  reduce/horner are latency-bound, few-thread kernels: they
   // run under the next group's accumulate; only the last group's reduce + Horner step is exposed.
+  // affine tree levels before the bucket kernel (msm_affine.cuh): by average bucket population
+  int LV = ctx->tune_msm_affine_levels;
+  if (LV < 0) {
+    size_t avg = sstride / (size_t)pl.nbuckets;
+    LV = avg >= 24 ? 3 : avg >= 12 ? 2 : avg >= 6 ? 1 : 0;
+  }
+  if (LV > 3) LV = 3;
   int gsz[16], ng = 0;
-  {
+  if (LV > 0 && pl.nloc >= 6) {
+    // fewer, larger groups so that the level kernels fill the GPU (16 -> 7 + 6 + 3)
+    gsz[ng++] = (pl.nloc * 7 + 8) / 16;
+    gsz[ng++] = ((pl.nloc - gsz[0]) * 2 + 2) / 3;
+    gsz[ng++] = pl.nloc - gsz[0] - gsz[1];
+  } else {
     int left = pl.nloc;
     if (left >= 12) {
       gsz[ng++] = (left * 3) / 8; left -= gsz[ng - 1];     // 16 -> 6
@@ -582,6 +605,31 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
       gsz[ng++] = left;
     } else {
       gsz[ng++] = left;
+    }
+  }
+  // scratch of the affine levels, sized for the largest group and reused by every group (main stream only)
+  constexpr size_t ABY = 2 * field_traits<F>::bytes;
+  uint32_t *lv_np = nullptr, *lv_po = nullptr, *lv_cnt[4] = {nullptr, nullptr, nullptr, nullptr},
+           *lv_off[4] = {nullptr, nullptr, nullptr, nullptr};
+  char *lv_buf[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t lv_cap[4] = {0, 0, 0, 0};
+  if (LV > 0) {
+    int maxg = 0;
+    for (int g = 0; g < ng; g++) maxg = gsz[g] > maxg ? gsz[g] : maxg;
+    size_t gt = (size_t)maxg * pl.nbuckets;
+    size_t extra = 2 * arena_pad(gt * 4);
+    for (int l = 1; l <= LV; l++) {
+      lv_cap[l] = (sstride >> l) + pl.nbuckets + 8;
+      extra += 2 * arena_pad(gt * 4) + arena_pad((size_t)maxg * lv_cap[l] * ABY);
+    }
+    // second, separately grown arena region: taken from the same arena (reserved above via `need`)
+    if (ctx->arena_off + extra > ctx->arena_size) return B200_ENOMEM;
+    lv_np = arena_take<uint32_t>(ctx, gt);
+    lv_po = arena_take<uint32_t>(ctx, gt);
+    for (int l = 1; l <= LV; l++) {
+      lv_cnt[l] = arena_take<uint32_t>(ctx, gt);
+      lv_off[l] = arena_take<uint32_t>(ctx, gt);
+      lv_buf[l] = arena_take<char>(ctx, (size_t)maxg * lv_cap[l] * ABY);
     }
   }
   // order the side streams after whatever is still queued on the main stream (previous calls)
@@ -613,11 +661,42 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
     // per-group scheduling scratch: SIZE_BINS-sized arrays are double-buffered by group parity
     uint32_t *sh = size_hist + (size_t)(g & 1) * 2 * SIZE_BINS, *sc = sh + SIZE_BINS;
     uint32_t *sb = size_base + (size_t)(g & 1) * SIZE_BINS;
+    // affine tree levels of this group
+    const uint32_t *cprev = hist + s0, *in_off = offsets + s0;
+    for (int l = 1; l <= LV; l++) {
+      int K = 64 >> (l - 1);
+      if (K < 8) K = 8;
+      B200_LAUNCH(ctx, k_aff_counts, nblk(gtotal, 256), 256, 0, gtotal, cprev, hist + s0, GIANT_BUCKET, lv_np, lv_cnt[l]);
+      B200_LAUNCH(ctx, k_msm_scan, cnt, 1024, 0, pl.nbuckets, lv_np, lv_po);
+      B200_LAUNCH(ctx, k_msm_scan, cnt, 1024, 0, pl.nbuckets, lv_cnt[l], lv_off[l]);
+      size_t maxpairs = (sstride >> l) + 1;
+      dim3 lgrid(nblk(maxpairs, (unsigned)K * 128u), cnt);
+      if (l == 1) {
+        B200_LAUNCH(ctx, (k_aff_level<F, true>), lgrid, 128, 0, pl.nbuckets, K, (const char *)points, (const char *)bx, sstride,
+                    in_off, sorted + (size_t)j_lo * sstride, (const char *)nullptr, (size_t)0, lv_np, lv_po, lv_off[l], lv_buf[l],
+                    lv_cap[l], ctx->inv_pow2);
+        B200_LAUNCH(ctx, (k_aff_leftover<F, true>), nblk(gtotal, 256), 256, 0, pl.nbuckets, gtotal, (const char *)points,
+                    (const char *)bx, sstride, cprev, hist + s0, GIANT_BUCKET, in_off, sorted + (size_t)j_lo * sstride,
+                    (const char *)nullptr, (size_t)0, lv_np, lv_off[l], lv_buf[l], lv_cap[l]);
+      } else {
+        B200_LAUNCH(ctx, (k_aff_level<F, false>), lgrid, 128, 0, pl.nbuckets, K, (const char *)points, (const char *)bx, sstride,
+                    in_off, (const uint32_t *)nullptr, (const char *)lv_buf[l - 1], lv_cap[l - 1], lv_np, lv_po, lv_off[l],
+                    lv_buf[l], lv_cap[l], ctx->inv_pow2);
+        B200_LAUNCH(ctx, (k_aff_leftover<F, false>), nblk(gtotal, 256), 256, 0, pl.nbuckets, gtotal, (const char *)points,
+                    (const char *)bx, sstride, cprev, hist + s0, GIANT_BUCKET, in_off, (const uint32_t *)nullptr,
+                    (const char *)lv_buf[l - 1], lv_cap[l - 1], lv_np, lv_off[l], lv_buf[l], lv_cap[l]);
+      }
+      cprev = lv_cnt[l];
+      in_off = lv_off[l];
+    }
     B200_CUDA(ctx, cudaMemsetAsync(sh, 0, 2 * SIZE_BINS * sizeof(uint32_t), ctx->stream));
-    B200_LAUNCH(ctx, k_msm_size_hist, nblk(gtotal, 256), 256, 0, gtotal, hist + s0, sh);
+    B200_LAUNCH(ctx, k_msm_size_hist, nblk(gtotal, 256), 256, 0, gtotal, cprev, hist + s0, sh);
     B200_LAUNCH(ctx, k_msm_size_scan, 1, SIZE_BINS, 0, sh, sb);
-    B200_LAUNCH(ctx, k_msm_size_scatter, nblk(gtotal, 256), 256, 0, gtotal, hist + s0, sb, sc, order + s0);
-    if constexpr (sizeof(F) == sizeof(fp)) {
+    B200_LAUNCH(ctx, k_msm_size_scatter, nblk(gtotal, 256), 256, 0, gtotal, cprev, hist + s0, sb, sc, order + s0);
+    if (LV > 0) {
+      B200_LAUNCH(ctx, (k_msm_accumulate_buf<F, (sizeof(F) == sizeof(fp) ? 3 : 2)>), nblk(gtotal, 128), 128, 0, pl.nbuckets, gtotal,
+                  s0, (const char *)lv_buf[LV], lv_cap[LV], lv_cnt[LV], lv_off[LV], hist, GIANT_BUCKET, order + s0, buckets);
+    } else if constexpr (sizeof(F) == sizeof(fp)) {
       if (ctx->tune_g1_prefetch) {
       B200_LAUNCH(ctx, (k_msm_accumulate<F, 3, true>), nblk(gtotal, 128), 128, 2 * 2 * field_traits<F>::bytes * 128, pl.nbuckets,
                   gtotal, s0, (const char *)points, bx, sstride, offsets, hist, sorted, order + s0, buckets);

@@ -27,6 +27,12 @@ struct b200_ctx {
   // thread-level parallelism of the bucket kernel (one 2^15-bucket window = 0.58 of a wave), which costs more than
   // the shorter reduction/Horner tail saves.  Kept as a knob for larger n / wider windows.
   int tune_g1_glv = 0;
+  // batched-affine tree levels in front of the bucket kernel (msm_affine.cuh): -1 auto by bucket population, 0..3.
+  // Implemented and parity-tested; OFF by default: at 2^20 (G1) measured 11.6 ms (2 levels) / 13.1 ms (3 levels) vs
+  // 9.0 ms for the pure XYZZ bucket kernel — every warp of a wave reaches its binary-GCD inversion (ALU pipe) at the
+  // same time instead of overlapping it with other warps' multiplications, and batches large enough to amortise it
+  // (K >= 128 pairs per thread) leave too few threads at this size.  Groundwork for larger N.
+  int tune_msm_affine_levels = 0;
   int tune_g1_prefetch = 1;    // G1 bucket kernel: cp.async double-buffered prefetch of the next point (1) or plain loads (0)
   int tune_pairing_chunks = 4; // independent Miller+final-exp chunks of a pairing batch kept in flight on 2 streams
   // G2 bucket kernel: 2 = accumulator in registers (255 regs, 2 blocks/SM); 3 = accumulator in shared memory, built
@@ -39,6 +45,7 @@ struct b200_ctx {
   // staging arena for the host-pointer entry points
   char *stage = nullptr;
   size_t stage_size = 0, stage_off = 0;
+  uint32_t *inv_pow2 = nullptr;  // table of fp_inv.cuh (769 x 12 words), filled at ctx creation
   // optional per-kernel timing (CUDA events on the ctx stream around every launch)
   bool timing = false;
   std::vector<cudaEvent_t> ev_pool;       // 2 per record

@@ -18,7 +18,7 @@ import numpy as np
 from . import _lib
 
 OPS = dict(mul=0, add=1, sub=2, square=3, neg=4, invert=5, frobenius=6, conjugate=7, mul_by_nonresidue=8,
-           cyclotomic_square=9)
+           cyclotomic_square=9, invert_fast=10)
 
 
 class B200Error(RuntimeError):

@@ -69,7 +69,8 @@ uint64_t b200_ctx_launch_count(const b200_ctx *ctx);
  * '\n' into `names`, and returns the number of records since the last set_timing call (>= 0). */
 int b200_ctx_set_timing(b200_ctx *ctx, int on);
 int b200_ctx_get_timing(b200_ctx *ctx, char *names, size_t names_len, float *ms, int max);
-/* tuning knobs by name: "msm_window" (0 = auto, else 2..24), "g1_glv" (0 off, 1 on, 2 auto = on for window-sharded calls), "g1_prefetch" (0|1), "g2_acc_blocks" (G2 bucket kernel variant: 2 registers,
+/* tuning knobs by name: "msm_window" (0 = auto, else 2..24), "g1_glv" (0 off, 1 on, 2 auto = on for window-sharded calls), "msm_affine_levels" (-1 auto, 0..3 batched-affine
+ * tree levels before the bucket kernel; default 0), "g1_prefetch" (0|1), "g2_acc_blocks" (G2 bucket kernel variant: 2 registers,
  * 3 shared-memory accumulator built for 3 blocks/SM, 4 shared-memory accumulator at 2 blocks/SM = default), "pairing_chunks" (1..64 independent chunks of a
  * pairing batch in flight).  Unknown key or bad value -> B200_EINVAL. */
 int b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int value);
@@ -81,7 +82,8 @@ int b200_ctx_set_msm_window(b200_ctx *ctx, int c);
 enum {
   B200_OP_MUL = 0, B200_OP_ADD = 1, B200_OP_SUB = 2, B200_OP_SQUARE = 3, B200_OP_NEG = 4,
   B200_OP_INVERT = 5, B200_OP_FROBENIUS = 6, B200_OP_CONJUGATE = 7, B200_OP_MUL_BY_NONRESIDUE = 8,
-  B200_OP_CYCLOTOMIC_SQUARE = 9
+  B200_OP_CYCLOTOMIC_SQUARE = 9,
+  B200_OP_INVERT_FAST = 10 /* Fp only: binary-GCD inverse (csrc/fp_inv.cuh), same value as B200_OP_INVERT */
 };
 /* out[i] = op(a[i], b[i]); b may be NULL for unary ops; arrays of n elements of 6*level u64 each */
 int b200_tower_op(b200_ctx *ctx, int level, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n);

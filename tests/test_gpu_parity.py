@@ -404,3 +404,50 @@ def test_msm_giant_buckets(eng, orc, k, n):
         exp = G.to_affine(G.msm_pippenger(xy, inf, s, c=12, threads=16))
         assert eq(got[0], exp[0]) and got[1][0] == exp[1][0], (k, variant)
         assert dt < 2.0, "giant buckets must not serialise on one thread (took %.2f s)" % dt
+
+
+def test_fp_invert_fast(eng, orc):
+    """binary-GCD inverse (csrc/fp_inv.cuh) == Fermat inverse == oracle, incl. 0, 1, p-1, R"""
+    rng = np.random.default_rng(1600)
+    a = np.concatenate([util.rand_fp(rng, 4000), util.edge_fp()])
+    got = eng.tower(1, "invert_fast", a)
+    assert eq(got, orc.tower(1, "invert", a))
+    assert eq(got, eng.tower(1, "invert", a))
+
+
+@pytest.mark.parametrize("k", [1, 2])
+@pytest.mark.parametrize("levels", [1, 2, 3])
+def test_msm_batched_affine_levels(eng, orc, k, levels):
+    """batched-affine tree levels in front of the bucket kernel (csrc/msm_affine.cuh): same group element, including
+    tangent pairs (P + P), cancelling pairs (P + (-P)), identity operands inside the tree, odd bucket populations,
+    empty buckets and giant buckets"""
+    rng = np.random.default_rng(1700 + k)
+    n = 900 if k == 1 else 500
+    _, xy, inf = util.rand_points(orc, k, rng, n)
+    s = util.rand_scalars(rng, n)
+    w = 6 * k
+    xy[5], s[5] = xy[4], s[4]                      # P + P at level 1 (adjacent only by chance -> several copies)
+    xy[6], s[6] = xy[4], s[4]
+    xy[7], s[7] = xy[4], s[4]
+    xy[9] = xy[8]
+    xy[9, w:] = orc.tower(k, "neg", xy[8, w:])
+    s[9] = s[8]                                    # P + (-P)
+    xy[11] = xy[10]
+    xy[11, w:] = orc.tower(k, "neg", xy[10, w:])
+    s[11] = s[10]
+    xy[12], s[12] = xy[10], s[10]                  # (P + (-P)) + P : identity operand at level 2
+    s[20:60] = s[20]                               # a crowded bucket
+    s[0] = 0
+    inf[30] = 1
+    eng.set_tuning("msm_affine_levels", levels)
+    try:
+        _msm_case(eng, orc, k, xy, inf, s, cs=(4, 6, 9))
+        _msm_case(eng, orc, k, xy[:3], inf[:3], s[:3], cs=(4,))
+        if levels == 3 and k == 1:                 # giant buckets next to the affine path
+            big = np.tile(xy[:64], (40, 1))
+            sb = np.repeat(s[100:101], 2560, 0)
+            sb[1280:] = rng.integers(0, 256, (1280, 32), dtype=np.uint8)
+            sb[1280:, 31] &= 0x3f
+            _msm_case(eng, orc, k, big, None, sb, cs=(4, 8))
+    finally:
+        eng.set_tuning("msm_affine_levels", 0)
