@@ -407,7 +407,7 @@ def main():
     if rank == 0:
         line = {"metric": UNIT[wl].replace("/s", "") + " per second", "value": value, "unit": UNIT[wl], "n_gpus": world,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-                "scaling": "weak" if wl in ("pairing", "g1_mul") and False else "strong", "vs_baseline": None,
+                "scaling": "strong", "vs_baseline": None,
                 "dtype": "u32x12 limbs (381-bit Montgomery, integer)", "data": "synthetic",
                 "config": {"workload": cfg_name, "n": n, "sharding": ("none" if world == 1 else
                            ("by pair/item index, no collective" if wl in ("pairing", "g1_mul") else
