@@ -132,6 +132,8 @@ def cpu_sample_size(workload, cores):
     # ~10-30 s of CPU work in total: reference cost/unit ~ FpM * 45 ns
     per_unit = {"g1_mul": 5100, "g1_msm": 5100, "g2_msm": 17085, "pairing": 16020}[workload] * 45e-9
     n = int(15.0 / per_unit)
+    if os.environ.get("B200_BENCH_CPU_SAMPLE"):        # tests shrink the sample (tests/test_bench_cli.py)
+        return int(os.environ["B200_BENCH_CPU_SAMPLE"])
     return max(64, min(n, 1 << 16))
 
 
