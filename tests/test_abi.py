@@ -41,3 +41,18 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no CPU fallback", ""), os.path.join(dirpath, f)
+
+
+def test_rust_sys_binding_covers_the_header():
+    """bindings/rust/bls12381-b200-sys/src/lib.rs is generated from the header (tools/gen_rust_sys.py): every
+    exported symbol must be bound, with the same number of parameters"""
+    rs = open(os.path.join(ROOT, "bindings", "rust", "bls12381-b200-sys", "src", "lib.rs")).read()
+    hdr = open(os.path.join(ROOT, "include", "bls12381_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    for sym in declared_symbols():
+        m = re.search(r"pub fn %s\(([^)]*)\)" % sym, rs)
+        assert m, "Rust binding misses %s" % sym
+        c = re.search(r"\b%s\s*\(([^;{]*?)\)\s*;" % sym, hdr)
+        nargs_c = len([a for a in c.group(1).split(",") if a.strip() and a.strip() != "void"])
+        nargs_rs = len([a for a in m.group(1).split(",") if a.strip()])
+        assert nargs_c == nargs_rs, sym

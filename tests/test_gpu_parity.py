@@ -451,3 +451,28 @@ def test_msm_batched_affine_levels(eng, orc, k, levels):
             _msm_case(eng, orc, k, big, None, sb, cs=(4, 8))
     finally:
         eng.set_tuning("msm_affine_levels", 0)
+
+
+@pytest.mark.parametrize("k", [1, 2])
+def test_msm_through_byte_encodings(eng, orc, k):
+    """the call sequence of the Rust wrapper (bindings/rust/bls12381-b200/src/lib.rs), which marshals ONLY through the
+    reference's public byte encodings: to_uncompressed bytes -> deserialize (GPU) -> MSM -> batch_normalize ->
+    serialize (GPU) == to_uncompressed(sum_i p_i * s_i) computed by the oracle"""
+    G = orc.G1 if k == 1 else orc.G2
+    rng = np.random.default_rng(1800 + k)
+    n = 150
+    _, xy, inf = util.rand_points(orc, k, rng, n)
+    inf[3] = 1
+    s = util.rand_scalars(rng, n)
+    enc = np.stack([G.to_uncompressed(xy[i], inf[i]) for i in range(n)])          # what G*Affine::to_uncompressed() gives
+    dxy, dinf, st = eng.deserialize(k, enc, compressed=False)
+    assert (st == 3).all()
+    res = eng.msm(k, dxy, dinf, s)
+    axy, ainf = eng.batch_normalize(k, res)
+    got = eng.serialize(k, axy, ainf, compressed=False)[0]
+    exp_aff = G.to_affine(G.msm_naive(xy, inf, s, threads=8))
+    assert np.array_equal(got, G.to_uncompressed(exp_aff[0][0], exp_aff[1][0]))
+    # and the batched validation of untrusted compressed encodings (from_compressed semantics: decode + subgroup)
+    cmp_ = np.stack([G.to_compressed(xy[i], inf[i]) for i in range(8)])
+    dxy, dinf, st = eng.deserialize(k, cmp_, compressed=True)
+    assert (st == 3).all() and (eng.check(k, dxy, dinf) == 3).all()
