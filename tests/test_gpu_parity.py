@@ -476,3 +476,33 @@ def test_msm_through_byte_encodings(eng, orc, k):
     cmp_ = np.stack([G.to_compressed(xy[i], inf[i]) for i in range(8)])
     dxy, dinf, st = eng.deserialize(k, cmp_, compressed=True)
     assert (st == 3).all() and (eng.check(k, dxy, dinf) == 3).all()
+
+
+def test_two_contexts_concurrently(orc):
+    """distinct b200_ctx are independent (Send + Sync on the Rust side): two engines driven from two host threads at
+    the same time give the same, correct results"""
+    import threading
+    import bls12_381_b200
+    rng = np.random.default_rng(1900)
+    _, xy, inf = util.rand_points(orc, 1, rng, 3000)
+    s = util.rand_scalars(rng, 3000)
+    exp = orc.G1.to_affine(orc.G1.msm_pippenger(xy, inf, s, c=10, threads=8))
+    results, errors = {}, []
+
+    def work(tag):
+        try:
+            e = bls12_381_b200.Engine()
+            for it in range(6):
+                got = orc.G1.to_affine(e.msm(1, xy, inf, s))
+                assert eq(got[0], exp[0]) and got[1][0] == exp[1][0], (tag, it)
+            results[tag] = True
+            e.close()
+        except Exception as ex:                      # noqa: BLE001
+            errors.append((tag, repr(ex)))
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors and len(results) == 2, errors
