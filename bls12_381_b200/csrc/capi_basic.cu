@@ -27,7 +27,7 @@ __global__ void k_tower_op(int op, const uint64_t *a, const uint64_t *b, uint64_
       case B200_OP_MUL: r = fp_mul(x, y); break;
       case B200_OP_ADD: r = fp_add(x, y); break;
       case B200_OP_SUB: r = fp_sub(x, y); break;
-      case B200_OP_SQUARE: r = fp_sqr(x); break;
+      case B200_OP_SQUARE: r = fp_sqr_c(x); break;   // the dedicated squaring the curve code uses
       case B200_OP_NEG: r = fp_neg(x); break;
       case B200_OP_INVERT_FAST: r = fp_inv_fast(x, pow2); break;
       default: r = fp_inv(x); break;

@@ -111,7 +111,7 @@ B200_DEV fp2 fp2_inv_ni(const fp2 &a) {
 B200_DEV fp f_add(const fp &a, const fp &b) { return fp_add(a, b); }
 B200_DEV fp f_sub(const fp &a, const fp &b) { return fp_sub(a, b); }
 B200_DEV fp f_mul(const fp &a, const fp &b) { return fp_mul_c(a, b); }
-B200_DEV fp f_sqr(const fp &a) { return fp_mul_c(a, a); }
+B200_DEV fp f_sqr(const fp &a) { return fp_sqr_c(a); }
 B200_DEV fp f_neg(const fp &a) { return fp_neg(a); }
 B200_DEV fp f_dbl(const fp &a) { return fp_dbl(a); }
 B200_DEV fp f_inv(const fp &a) { return fp_inv(a); }
