@@ -39,7 +39,9 @@ int final_exp_dev(b200_ctx *ctx, const void *in, size_t n, void *out) { return f
 int pairing_dev(b200_ctx *ctx, const void *p, const void *pi, const void *q, const void *qi, size_t n, void *out) {
   int chunks = ctx->tune_pairing_chunks;
   if (chunks < 1) chunks = 1;
-  if (n < (size_t)chunks * 4096) chunks = 1;
+  // chunking only pays when the batch exceeds one wave of resident threads (148 SMs x 4 blocks x 64 = 37 888): below
+  // that a single launch per kernel is already one (partial) wave, and smaller launches only add latency
+  if (n <= (size_t)ctx->sm_count * 4 * 64 + 2048) chunks = 1;
   if (chunks == 1) {
     int rc = miller_dev(ctx, p, pi, q, qi, n, out);
     return rc != B200_OK ? rc : final_exp_dev(ctx, out, n, out);
