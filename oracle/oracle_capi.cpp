@@ -53,7 +53,7 @@ extern "C" {
 int orc_tower_op(int level, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n) {
   for (size_t i = 0; i < n; i++) {
     if (level == 1) {
-      Fp x, y, r;
+      Fp x{}, y{}, r{};
       std::memcpy(&x, a + 6 * i, 48);
       if (b) std::memcpy(&y, b + 6 * i, 48);
       switch (op) {
@@ -67,7 +67,7 @@ int orc_tower_op(int level, int op, const uint64_t *a, const uint64_t *b, uint64
       }
       std::memcpy(out + 6 * i, &r, 48);
     } else if (level == 2) {
-      Fp2 x, y, r;
+      Fp2 x{}, y{}, r{};
       std::memcpy(&x, a + 12 * i, 96);
       if (b) std::memcpy(&y, b + 12 * i, 96);
       switch (op) {
@@ -84,7 +84,7 @@ int orc_tower_op(int level, int op, const uint64_t *a, const uint64_t *b, uint64
       }
       std::memcpy(out + 12 * i, &r, 96);
     } else if (level == 6) {
-      Fp6 x, y, r;
+      Fp6 x{}, y{}, r{};
       std::memcpy(&x, a + 36 * i, 288);
       if (b) std::memcpy(&y, b + 36 * i, 288);
       switch (op) {
@@ -100,7 +100,7 @@ int orc_tower_op(int level, int op, const uint64_t *a, const uint64_t *b, uint64
       }
       std::memcpy(out + 36 * i, &r, 288);
     } else if (level == 12) {
-      Fp12 x, y, r;
+      Fp12 x{}, y{}, r{};
       std::memcpy(&x, a + 72 * i, 576);
       if (b) std::memcpy(&y, b + 72 * i, 576);
       switch (op) {
