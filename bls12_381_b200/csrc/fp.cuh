@@ -73,6 +73,9 @@ B200_DEV fp fp_zero() {
 }
 
 // ---- PTX carry-chain primitives (CC.CF lives between adjacent volatile asm statements)
+#ifdef B200_HOST_EMUL  // CPU test harness (tests/emul/): bit-exact C models of the same instructions
+#include "emul_ptx.h"
+#else
 B200_DEV void ptx_add_cc(uint32_t &d, uint32_t a, uint32_t b) { asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
 B200_DEV void ptx_addc_cc(uint32_t &d, uint32_t a, uint32_t b) { asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
 B200_DEV void ptx_addc(uint32_t &d, uint32_t a, uint32_t b) { asm volatile("addc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
@@ -85,6 +88,7 @@ B200_DEV void ptx_mad_lo_cc(uint32_t &d, uint32_t a, uint32_t b, uint32_t c) { a
 B200_DEV void ptx_madc_lo_cc(uint32_t &d, uint32_t a, uint32_t b, uint32_t c) { asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); }
 B200_DEV void ptx_madc_hi_cc(uint32_t &d, uint32_t a, uint32_t b, uint32_t c) { asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); }
 B200_DEV void ptx_madc_hi(uint32_t &d, uint32_t a, uint32_t b, uint32_t c) { asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); }
+#endif
 
 // acc[0..12) += x[0],x[2],..,x[10] (stride-2 words of a 12-word operand starting at x) * s ; one
 // carry chain; the carry out of acc[11] is left in CC.CF for the caller.

@@ -1,0 +1,34 @@
+"""TEST INFRASTRUCTURE: compiles the device headers of bls12_381_b200/csrc for the host (see cuda_host_shim.h)."""
+import hashlib
+import os
+import subprocess
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(os.path.dirname(_DIR))
+_CSRC = os.path.join(_ROOT, "bls12_381_b200", "csrc")
+
+
+def _digest(extra):
+    h = hashlib.sha256(extra.encode())
+    for d in (_DIR, _CSRC):
+        for f in sorted(os.listdir(d)):
+            if f.endswith((".cuh", ".h", ".cpp", ".inc")):
+                h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()
+
+
+def build(variant="default"):
+    """variant: 'default' (lazy-reduction Fp2: capi_basic/capi_msm/capi_serial) or 'kcall' (pairing units)"""
+    so = os.path.join(_DIR, "libemul_%s.so" % variant)
+    flags = ["-DB200_FP2_KCALL"] if variant == "kcall" else []
+    if os.path.exists(os.path.join(_CSRC, "fr.cuh")):
+        flags.append("-DEMUL_WITH_FR")
+    stamp = so + ".stamp"
+    dg = _digest(" ".join(flags))
+    if os.path.exists(so) and os.path.exists(stamp) and open(stamp).read() == dg:
+        return so
+    cmd = ["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-pthread", "-Wno-unknown-pragmas", "-I", _DIR, "-I", _CSRC,
+           "-I", os.path.join(_ROOT, "include")] + flags + [os.path.join(_DIR, "emul_capi.cpp"), "-o", so]
+    subprocess.check_call(cmd)
+    open(stamp, "w").write(dg)
+    return so

@@ -1,0 +1,53 @@
+// TEST INFRASTRUCTURE.  Lets g++ compile the device-side headers of bls12_381_b200/csrc/ (fp.cuh ... pairing.cuh)
+// as plain C++ so the CPU suite (-m "not gpu") can run the SAME source the GPU runs — limb algorithms, tower,
+// curve formulas, Miller loop, final exponentiation — against the oracle.  What it does NOT cover: the PTX -> SASS
+// path, launch geometry, warp/CTA cooperation and memory staging; those are the job of the -m gpu tests.
+//
+//   * CUDA qualifiers become no-ops, threadIdx/blockIdx/... are thread-local variables a host loop steps through
+//     (only kernels without intra-block cooperation can be run that way);
+//   * the PTX carry-chain primitives of fp.cuh are replaced by bit-exact C models (emul_ptx.h) with an explicit
+//     carry flag: add.cc/addc/sub.cc/subc/mad{c}.{lo,hi}{.cc} as defined in the PTX ISA ("Extended-Precision
+//     Integer Arithmetic": CC.CF is the carry-out of add/mad and the borrow-out of sub).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include <algorithm>   // all standard headers BEFORE the qualifier macros (libstdc++ uses __noinline__ itself)
+#include <vector>
+#include <thread>
+
+#define B200_HOST_EMUL 1
+#define __device__
+#define __host__
+#define __global__
+#define __constant__
+#define __forceinline__ inline
+#define __noinline__ __attribute__((noinline))
+#define __launch_bounds__(...)
+#define __restrict__
+
+struct uint4 {
+  uint32_t x, y, z, w;
+};
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+struct emul_dim3 {
+  unsigned x = 1, y = 1, z = 1;
+};
+static thread_local emul_dim3 threadIdx, blockIdx, blockDim, gridDim;
+
+template <class T>
+static inline T __ldg(const T *p) { return *p; }
+static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t s) {
+  uint64_t v = ((uint64_t)hi << 32) | lo;
+  return (uint32_t)((v << (s & 31)) >> 32);
+}
+static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t s) {
+  uint64_t v = ((uint64_t)hi << 32) | lo;
+  return (uint32_t)(v >> (s & 31));
+}
+static inline int __clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
+static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
+static inline int __ffs(uint32_t x) { return __builtin_ffs((int)x); }
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+using std::min;
+using std::max;

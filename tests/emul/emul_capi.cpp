@@ -1,0 +1,199 @@
+// TEST INFRASTRUCTURE.  The device-side arithmetic of bls12_381_b200/csrc/ compiled for the HOST (see cuda_host_shim.h)
+// behind a flat C API that mirrors include/bls12381_b200.h's array conventions, so tests/test_device_source_cpu.py can
+// compare it with the oracle without a GPU.  Built twice: default (lazy-reduction Fp2, the G2/MSM translation units)
+// and -DB200_FP2_KCALL (the pairing translation units).
+#include "cuda_host_shim.h"
+
+#include "curve.cuh"
+#include "fp_inv.cuh"
+#include "glv.cuh"
+#include "pairing.cuh"
+#ifdef EMUL_WITH_FR
+#include "fr.cuh"
+#endif
+
+using namespace b200;
+
+namespace {
+std::vector<uint32_t> &pow2_table() {
+  static std::vector<uint32_t> t;
+  if (t.empty()) {
+    t.resize(FP_INV_TABLE_WORDS);
+    threadIdx = emul_dim3{0, 0, 0};
+    blockIdx = emul_dim3{0, 0, 0};
+    k_fp_inv_table_init(t.data());
+  }
+  return t;
+}
+template <class Fn>
+void par_for(size_t n, int threads, Fn fn) {
+  if (threads <= 1 || n < 2) {
+    for (size_t i = 0; i < n; i++) fn(i);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (int t = 0; t < threads; t++)
+    th.emplace_back([=] {
+      for (size_t i = t; i < n; i += threads) fn(i);
+    });
+  for (auto &x : th) x.join();
+}
+}  // namespace
+
+extern "C" {
+
+// op codes of include/bls12381_b200.h (B200_OP_*); extra codes >= 100 select implementation variants of Fp mul/sqr
+int emul_tower_op(int level, int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n) {
+  const uint32_t *pow2 = pow2_table().data();
+  const int W = 6 * level;
+  for (size_t i = 0; i < n; i++) {
+    const uint64_t *pa = a + W * i, *pb = b ? b + W * i : nullptr;
+    uint64_t *po = out + W * i;
+    if (level == 1) {
+      fp x = fp_load(pa), y = pb ? fp_load(pb) : fp_zero(), r;
+      switch (op) {
+        case 0: r = fp_mul(x, y); break;
+        case 1: r = fp_add(x, y); break;
+        case 2: r = fp_sub(x, y); break;
+        case 3: r = fp_sqr_c(x); break;
+        case 4: r = fp_neg(x); break;
+        case 5: r = fp_inv(x); break;
+        case 10: r = fp_inv_fast(x, pow2); break;
+        case 100: r = fp_mul_c(x, y); break;
+        case 101: r = fp_redc_wide(fp_mul_wide(x, y)); break;
+        case 102: r = fp_sqr(x); break;
+        case 103: r = fp_add_nr(x, y); break;  // caller keeps x + y < 2^384
+        default: return -1;
+      }
+      fp_store(po, r);
+    } else if (level == 2) {
+      fp2 x = fp2_load(pa), y = pb ? fp2_load(pb) : fp2_zero(), r;
+      switch (op) {
+        case 0: r = M2(x, y); break;
+        case 1: r = fp2_add(x, y); break;
+        case 2: r = fp2_sub(x, y); break;
+        case 3: r = S2(x); break;
+        case 4: r = fp2_neg(x); break;
+        case 5: r = fp2_inv(x); break;
+        case 6: case 7: r = fp2_conj(x); break;
+        case 8: r = fp2_mul_by_nonresidue(x); break;
+        case 100: r = fp2_mul(x, y); break;
+        case 101: r = fp2_sqr(x); break;
+        case 102: r = fp2_inv_ni(x); break;
+        default: return -1;
+      }
+      fp2_store(po, r);
+    } else if (level == 6) {
+      fp6 x, y, r;
+      fp6_load(&x, pa);
+      if (pb) fp6_load(&y, pb);
+      switch (op) {
+        case 0: fp6_mul(&r, &x, &y); break;
+        case 1: fp6_add(&r, &x, &y); break;
+        case 2: fp6_sub(&r, &x, &y); break;
+        case 3: fp6_sqr(&r, &x); break;
+        case 4: fp6_neg(&r, &x); break;
+        case 5: fp6_inv(&r, &x); break;
+        case 6: fp6_frobenius(&r, &x); break;
+        case 8: fp6_mul_by_nonresidue(&r, &x); break;
+        default: return -1;
+      }
+      fp6_store(po, &r);
+    } else if (level == 12) {
+      fp12 x, y, r;
+      fp12_load(&x, pa);
+      if (pb) fp12_load(&y, pb);
+      switch (op) {
+        case 0: fp12_mul(&r, &x, &y); break;
+        case 3: fp12_sqr(&r, &x); break;
+        case 5: fp12_inv(&r, &x); break;
+        case 6: fp12_frobenius(&r, &x); break;
+        case 7: fp12_conj(&r, &x); break;
+        case 9: cyclotomic_square(&r, &x); break;
+        default: return -1;
+      }
+      fp12_store(po, &r);
+    } else {
+      return -1;
+    }
+  }
+  return 0;
+}
+
+#define GROUP_API(NAME, F)                                                                                            \
+  void emul_##NAME##_double(const char *p, char *out, size_t n) {                                                     \
+    constexpr size_t PB = 3 * field_traits<F>::bytes;                                                                 \
+    for (size_t i = 0; i < n; i++) proj_store<F>(out + PB * i, proj_double(proj_load<F>(p + PB * i)));                 \
+  }                                                                                                                   \
+  void emul_##NAME##_add(const char *p, const char *q, char *out, size_t n) {                                         \
+    constexpr size_t PB = 3 * field_traits<F>::bytes;                                                                 \
+    for (size_t i = 0; i < n; i++)                                                                                    \
+      proj_store<F>(out + PB * i, proj_add(proj_load<F>(p + PB * i), proj_load<F>(q + PB * i)));                       \
+  }                                                                                                                   \
+  void emul_##NAME##_add_mixed(const char *p, const char *qxy, const uint8_t *qinf, char *out, size_t n) {            \
+    constexpr size_t PB = 3 * field_traits<F>::bytes;                                                                 \
+    for (size_t i = 0; i < n; i++)                                                                                    \
+      proj_store<F>(out + PB * i, proj_add_mixed(proj_load<F>(p + PB * i), affine_load<F>(qxy, qinf, i)));             \
+  }                                                                                                                   \
+  void emul_##NAME##_mul(const char *p, const uint32_t *s, char *out, size_t n, int threads) {                        \
+    constexpr size_t PB = 3 * field_traits<F>::bytes;                                                                 \
+    par_for(n, threads, [=](size_t i) {                                                                               \
+      uint32_t by[8];                                                                                                 \
+      memcpy(by, s + 8 * i, 32);                                                                                      \
+      proj_store<F>(out + PB * i, proj_multiply(proj_load<F>(p + PB * i), by));                                        \
+    });                                                                                                               \
+  }                                                                                                                   \
+  void emul_##NAME##_to_affine(const char *p, char *xy, uint8_t *inf, size_t n) {                                     \
+    constexpr size_t PB = 3 * field_traits<F>::bytes;                                                                 \
+    for (size_t i = 0; i < n; i++) affine_store<F>(xy, inf, i, proj_to_affine(proj_load<F>(p + PB * i)));              \
+  }                                                                                                                   \
+  /* the bucket accumulator of the MSM: fold affine points into one XYZZ sum, in order */                             \
+  void emul_##NAME##_xyzz_sum(const char *xy, const uint8_t *inf, size_t n, char *out) {                              \
+    xyzz<F> acc = xyzz_identity<F>();                                                                                 \
+    for (size_t i = 0; i < n; i++) {                                                                                  \
+      affine<F> a = affine_load<F>(xy, inf, i);                                                                       \
+      if (a.inf) continue;                                                                                            \
+      acc = xyzz_add_mixed(acc, a.x, a.y);                                                                            \
+    }                                                                                                                 \
+    proj_store<F>(out, xyzz_to_proj(acc));                                                                            \
+  }
+GROUP_API(g1, fp)
+GROUP_API(g2, fp2)
+
+void emul_miller_loop(const char *pxy, const uint8_t *pinf, const char *qxy, const uint8_t *qinf, size_t n, uint64_t *out,
+                      int threads) {
+  par_for(n, threads, [=](size_t i) {
+    fp12 f;
+    miller_loop_pair(&f, affine_load<fp>(pxy, pinf, i), affine_load<fp2>(qxy, qinf, i));
+    fp12_store(out + 72 * i, &f);
+  });
+}
+void emul_final_exponentiation(const uint64_t *in, size_t n, uint64_t *out, int threads) {
+  par_for(n, threads, [=](size_t i) {
+    fp12 f;
+    fp12_load(&f, in + 72 * i);
+    final_exponentiation(&f);
+    fp12_store(out + 72 * i, &f);
+  });
+}
+void emul_g2_prepare(const char *qxy, int qinf, char *coeffs /* 68 * 288 B */) {
+  uint8_t flag = qinf ? 1 : 0;
+  g2_prepare(affine_load<fp2>(qxy, &flag, 0), coeffs);
+}
+void emul_miller_loop_prepared(const char *pxy, int pinf, const char *coeffs, int qinf, uint64_t *out) {
+  uint8_t flag = pinf ? 1 : 0;
+  fp12 f;
+  miller_loop_prepared(&f, affine_load<fp>(pxy, &flag, 0), coeffs, qinf != 0);
+  fp12_store(out, &f);
+}
+// out: k1[4] k2[4] neg1 neg2 (10 words per scalar)
+void emul_glv_decompose(const uint32_t *s, size_t n, uint32_t *out) {
+  for (size_t i = 0; i < n; i++) {
+    glv_parts g = glv_decompose(s + 8 * i);
+    memcpy(out + 10 * i, g.k1, 16);
+    memcpy(out + 10 * i + 4, g.k2, 16);
+    out[10 * i + 8] = g.neg1;
+    out[10 * i + 9] = g.neg2;
+  }
+}
+}  // extern "C"
