@@ -479,6 +479,89 @@ static inline Scalar fr_from_bytes_wide(const uint8_t b[64]) {
   return fr_add(fr_mul(d0, FR_R2), fr_mul(d1, FR_R3));
 }
 
+// ----------------------------------------------------------------- Scalar field arithmetic
+// src/scalar.rs:159-164 (R = Scalar::one()), :183-188 (TWO_INV), :191 (S), :200-205 (ROOT_OF_UNITY),
+// :208-213 (ROOT_OF_UNITY_INV), :100-105 (GENERATOR = 7)
+static const Scalar FR_ONE = {{0x00000001fffffffeULL, 0x5884b7fa00034802ULL, 0x998c4fefecbc4ff5ULL, 0x1824b159acc5056fULL}};
+static const Scalar FR_TWO_INV = {{0x00000000ffffffffULL, 0xac425bfd0001a401ULL, 0xccc627f7f65e27faULL, 0x0c1258acd66282b7ULL}};
+static const Scalar FR_ROOT_OF_UNITY = {{0xb9b58d8c5f0e466aULL, 0x5b1b4c801819d7ecULL, 0x0af53ae352a31e64ULL, 0x5bf3adda19e9b27bULL}};
+static const Scalar FR_ROOT_OF_UNITY_INV = {{0x4256481adcf3219aULL, 0x45f37b7f96b6cad3ULL, 0xf9c3f1d75f7a3b27ULL, 0x2d2fc049658afd43ULL}};
+static const Scalar FR_GENERATOR = {{0x0000000efffffff1ULL, 0x17e363d300189c0fULL, 0xff9c57876f8457b0ULL, 0x351332208fc5a8c4ULL}};
+static const int FR_S = 32;
+static inline Scalar fr_zero() { return Scalar{{0, 0, 0, 0}}; }
+static inline bool fr_is_zero(const Scalar &a) { return (a.l[0] | a.l[1] | a.l[2] | a.l[3]) == 0; }
+static inline bool fr_eq(const Scalar &a, const Scalar &b) {
+  return a.l[0] == b.l[0] && a.l[1] == b.l[1] && a.l[2] == b.l[2] && a.l[3] == b.l[3];
+}
+static inline Scalar fr_sub(const Scalar &a, const Scalar &b) {  // src/scalar.rs:582-597
+  u64 borrow = 0, d[4];
+  for (int i = 0; i < 4; i++) d[i] = sbb(a.l[i], b.l[i], borrow);
+  Scalar r;
+  u64 carry = 0;
+  for (int i = 0; i < 4; i++) r.l[i] = adc(d[i], FR_MODULUS[i] & borrow, carry);
+  return r;
+}
+static inline Scalar fr_neg(const Scalar &a) {  // src/scalar.rs:613-627
+  u64 borrow = 0, d[4];
+  for (int i = 0; i < 4; i++) d[i] = sbb(FR_MODULUS[i], a.l[i], borrow);
+  u64 mask = fr_is_zero(a) ? 0 : ~(u64)0;
+  return Scalar{{d[0] & mask, d[1] & mask, d[2] & mask, d[3] & mask}};
+}
+static inline Scalar fr_mul(const Scalar &a, const Scalar &b) { return fr_mul(a, b.l); }
+// src/scalar.rs:341-370 (dedicated squaring; the same canonical value as mul(a, a), which is what is computed here)
+static inline Scalar fr_square(const Scalar &a) { return fr_mul(a, a.l); }
+static inline Scalar fr_double(const Scalar &a) { return fr_add(a, a); }  // src/scalar.rs:249-252
+// src/scalar.rs:392-404
+static inline Scalar fr_pow_vartime(const Scalar &a, const u64 by[4]) {
+  Scalar res = FR_ONE;
+  for (int w = 3; w >= 0; w--)
+    for (int i = 63; i >= 0; i--) {
+      res = fr_square(res);
+      if ((by[w] >> i) & 1) res = fr_mul(res, a);
+    }
+  return res;
+}
+// src/scalar.rs:408-503 computes a^(q-2) with a fixed addition chain; the reference's own test_invert_is_pow
+// (:1184-1208) pins invert() == pow_vartime(q - 2), which is what is restated here.  0 -> 0 with ok = false.
+static inline Scalar fr_invert(const Scalar &a, bool *ok = nullptr) {
+  static const u64 QM2[4] = {0xfffffffeffffffffULL, 0x53bda402fffe5bfeULL, 0x3339d80809a1d805ULL, 0x73eda753299d7d48ULL};
+  if (ok) *ok = !fr_is_zero(a);
+  return fr_pow_vartime(a, QM2);
+}
+// src/scalar.rs:256-281 ; returns false when the encoding is not canonical (>= q)
+static inline bool fr_from_bytes(const uint8_t b[32], Scalar &out) {
+  Scalar t;
+  for (int i = 0; i < 4; i++) {
+    u64 v = 0;
+    for (int k = 7; k >= 0; k--) v = (v << 8) | b[i * 8 + k];
+    t.l[i] = v;
+  }
+  u64 borrow = 0;
+  for (int i = 0; i < 4; i++) (void)sbb(t.l[i], FR_MODULUS[i], borrow);
+  out = fr_mul(t, FR_R2);
+  return (borrow & 1) != 0;
+}
+// w_n = ROOT_OF_UNITY^(2^(S - log_n)): the primitive 2^log_n-th root of unity every FFT over this field is built
+// on (src/scalar.rs:191-205).  The reference exports the constant, not a transform; the transform below is the
+// textbook definition  out[k] = sum_j a[j] w_n^(jk)  that downstream provers (bellman's EvaluationDomain) compute.
+static inline Scalar fr_omega(int log_n, bool inverse) {
+  Scalar w = inverse ? FR_ROOT_OF_UNITY_INV : FR_ROOT_OF_UNITY;
+  for (int i = log_n; i < FR_S; i++) w = fr_square(w);
+  return w;
+}
+static inline void fr_dft_naive(const Scalar *a, Scalar *out, size_t n, const Scalar &w) {
+  Scalar wk = FR_ONE;  // w^k
+  for (size_t k = 0; k < n; k++) {
+    Scalar acc = fr_zero(), x = FR_ONE;  // x = w^(jk)
+    for (size_t j = 0; j < n; j++) {
+      acc = fr_add(acc, fr_mul(a[j], x));
+      x = fr_mul(x, wk);
+    }
+    out[k] = acc;
+    wk = fr_mul(wk, w);
+  }
+}
+
 // ================================================================= G1 (src/g1.rs)
 struct G1Affine {
   Fp x, y;

@@ -177,6 +177,128 @@ void orc_scalar_to_bytes(const uint64_t *mont, uint8_t *out32, size_t n) {
   }
 }
 
+// ---------------------------------------------------------------- scalar field
+// op: 0 mul 1 add 2 sub 3 square 4 neg 5 invert (0 -> 0) 11 double; Montgomery limbs (4 x u64) in and out
+int orc_fr_op(int op, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n, int threads) {
+  if (op != 0 && op != 1 && op != 2 && op != 3 && op != 4 && op != 5 && op != 11) return -1;
+  parallel_for(n, threads, [&](size_t i) {
+    Scalar x{}, y{}, r{};
+    std::memcpy(&x, a + 4 * i, 32);
+    if (b) std::memcpy(&y, b + 4 * i, 32);
+    switch (op) {
+      case 0: r = fr_mul(x, y); break;
+      case 1: r = fr_add(x, y); break;
+      case 2: r = fr_sub(x, y); break;
+      case 3: r = fr_square(x); break;
+      case 4: r = fr_neg(x); break;
+      case 5: r = fr_invert(x); break;
+      default: r = fr_double(x); break;
+    }
+    std::memcpy(out + 4 * i, &r, 32);
+  });
+  return 0;
+}
+// Scalar::from_bytes: ok[i] = 1 when canonical; the limbs are written either way (like the CtOption's inner value)
+void orc_fr_from_bytes(const uint8_t *in32, uint64_t *mont, uint8_t *ok, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    Scalar s{};
+    ok[i] = fr_from_bytes(in32 + 32 * i, s) ? 1 : 0;
+    std::memcpy(mont + 4 * i, &s, 32);
+  }
+}
+void orc_fr_pow(const uint64_t *a, const uint64_t *by, uint64_t *out) {
+  Scalar x{};
+  std::memcpy(&x, a, 32);
+  Scalar r = fr_pow_vartime(x, by);
+  std::memcpy(out, &r, 32);
+}
+void orc_fr_const(int which, uint64_t *out) {  // 0 one, 1 two_inv, 2 root_of_unity, 3 root_of_unity_inv, 4 generator
+  const Scalar *c[] = {&FR_ONE, &FR_TWO_INV, &FR_ROOT_OF_UNITY, &FR_ROOT_OF_UNITY_INV, &FR_GENERATOR};
+  std::memcpy(out, c[which], 32);
+}
+// out[k] = sum_j a[j] w^(jk) by the O(n^2) definition, w = ROOT_OF_UNITY^(2^(32 - log_n)) (its inverse when `inverse`;
+// the inverse transform also divides by n).  coset: forward evaluates on g*<w> (a[j] *= g^j first), inverse undoes it.
+void orc_fr_dft_naive(const uint64_t *a, int log_n, int inverse, int coset, uint64_t *out) {
+  size_t n = (size_t)1 << log_n;
+  std::vector<Scalar> x(n), y(n);
+  std::memcpy(x.data(), a, 32 * n);
+  Scalar g = FR_GENERATOR;
+  if (coset && !inverse) {
+    Scalar p = FR_ONE;
+    for (size_t j = 0; j < n; j++) {
+      x[j] = fr_mul(x[j], p);
+      p = fr_mul(p, g);
+    }
+  }
+  fr_dft_naive(x.data(), y.data(), n, fr_omega(log_n, inverse != 0));
+  if (inverse) {
+    Scalar ninv = FR_ONE;
+    for (int i = 0; i < log_n; i++) ninv = fr_mul(ninv, FR_TWO_INV);
+    Scalar ginv = fr_invert(g), p = FR_ONE;
+    for (size_t j = 0; j < n; j++) {
+      y[j] = fr_mul(y[j], ninv);
+      if (coset) {
+        y[j] = fr_mul(y[j], p);
+        p = fr_mul(p, ginv);
+      }
+    }
+  }
+  std::memcpy(out, y.data(), 32 * n);
+}
+// the same transform in O(n log n): bit-reversal permutation, then log_n butterfly stages (decimation in time);
+// stage t pairs (i, i + 2^t) with twiddle w^((i mod 2^t) * n / 2^(t+1)).  The CPU baseline of bench.py's fr_ntt
+// workload and the oracle for sizes the definition above is too slow for.
+void orc_fr_ntt(const uint64_t *a, int log_n, int inverse, int coset, uint64_t *out, int threads) {
+  size_t n = (size_t)1 << log_n;
+  std::vector<Scalar> x(n);
+  Scalar g = FR_GENERATOR;
+  {
+    const Scalar *in = reinterpret_cast<const Scalar *>(a);
+    std::vector<Scalar> gp;
+    if (coset && !inverse) {
+      gp.resize(n);
+      Scalar p = FR_ONE;
+      for (size_t j = 0; j < n; j++) {
+        gp[j] = p;
+        p = fr_mul(p, g);
+      }
+    }
+    for (size_t i = 0; i < n; i++) {
+      size_t r = 0;
+      for (int b = 0; b < log_n; b++) r |= ((i >> b) & 1) << (log_n - 1 - b);
+      Scalar v;
+      std::memcpy(&v, &in[r], 32);
+      x[i] = gp.empty() ? v : fr_mul(v, gp[r]);
+    }
+  }
+  Scalar w = fr_omega(log_n, inverse != 0);
+  std::vector<Scalar> tw(n > 1 ? n / 2 : 1);
+  tw[0] = FR_ONE;
+  for (size_t e = 1; e < n / 2; e++) tw[e] = fr_mul(tw[e - 1], w);
+  for (int t = 0; t < log_n; t++) {
+    size_t half = (size_t)1 << t, step = n >> (t + 1);
+    parallel_for(n / 2, threads, [&](size_t k) {
+      size_t lo = k & (half - 1), i = ((k >> t) << (t + 1)) | lo;
+      Scalar u = x[i], v = fr_mul(x[i + half], tw[lo * step]);
+      x[i] = fr_add(u, v);
+      x[i + half] = fr_sub(u, v);
+    });
+  }
+  if (inverse) {
+    Scalar ninv = FR_ONE;
+    for (int i = 0; i < log_n; i++) ninv = fr_mul(ninv, FR_TWO_INV);
+    Scalar ginv = fr_invert(g), p = FR_ONE;
+    for (size_t j = 0; j < n; j++) {
+      x[j] = fr_mul(x[j], ninv);
+      if (coset) {
+        x[j] = fr_mul(x[j], p);
+        p = fr_mul(p, ginv);
+      }
+    }
+  }
+  std::memcpy(out, x.data(), 32 * n);
+}
+
 // ---------------------------------------------------------------- G1
 void orc_g1_generator(uint64_t *proj) {
   G1Projective g = g1p_generator();

@@ -127,6 +127,58 @@ def scalar_to_bytes(mont):
     return out
 
 
+FR_OPS = dict(mul=0, add=1, sub=2, square=3, neg=4, invert=5, double=11)
+
+
+def fr_op(op, a, b=None, threads=1):
+    """Scalar-field ops on Montgomery limbs (n,4) uint64  (src/scalar.rs:554-627, :341, :408, :249)"""
+    a = _u64(a, 4)
+    b = None if b is None else _u64(b, 4)
+    out = np.empty_like(a)
+    rc = lib().orc_fr_op(FR_OPS[op], _p(a), _p(b), _p(out), C.c_size_t(a.shape[0]), threads)
+    assert rc == 0
+    return out
+
+
+def fr_from_bytes(b):
+    b = _u8(b, 32)
+    out = np.empty((b.shape[0], 4), np.uint64)
+    ok = np.empty(b.shape[0], np.uint8)
+    lib().orc_fr_from_bytes(_p(b), _p(out), _p(ok), C.c_size_t(b.shape[0]))
+    return out, ok
+
+
+def fr_pow(a, by):
+    a, by = _u64(a, 4), _u64(by, 4)
+    out = np.empty((1, 4), np.uint64)
+    lib().orc_fr_pow(_p(a), _p(by), _p(out))
+    return out
+
+
+def fr_const(name):
+    out = np.empty((1, 4), np.uint64)
+    lib().orc_fr_const(dict(one=0, two_inv=1, root_of_unity=2, root_of_unity_inv=3, generator=4)[name], _p(out))
+    return out
+
+
+def fr_dft_naive(a, inverse=False, coset=False):
+    a = _u64(a, 4)
+    log_n = int(a.shape[0]).bit_length() - 1
+    assert a.shape[0] == 1 << log_n
+    out = np.empty_like(a)
+    lib().orc_fr_dft_naive(_p(a), log_n, int(inverse), int(coset), _p(out))
+    return out
+
+
+def fr_ntt(a, inverse=False, coset=False, threads=1):
+    a = _u64(a, 4)
+    log_n = int(a.shape[0]).bit_length() - 1
+    assert a.shape[0] == 1 << log_n
+    out = np.empty_like(a)
+    lib().orc_fr_ntt(_p(a), log_n, int(inverse), int(coset), _p(out), threads)
+    return out
+
+
 class _Group:
     """G1 (k=1) or G2 (k=2) entry points; coordinates are k*6 limbs wide."""
 

@@ -44,7 +44,7 @@ KATS = {
     "g1.rs": (6, ["test_doubling", "test_projective_addition", "test_mixed_addition", "test_beta", "test_is_torsion_free"]),
     "g2.rs": (6, ["test_doubling", "test_projective_addition", "test_mixed_addition", "test_is_torsion_free"]),
     "pairings.rs": (6, ["generator"]),           # Gt::generator(), src/pairings.rs:359-475
-    "scalar.rs": (4, ["test_from_bytes_wide_maximum"]),
+    "scalar.rs": (4, ["test_from_bytes_wide_maximum", "test_addition", "test_double"]),
     "tests/mod.rs": (6, ["test_pairing_result_against_relic"]),   # expected Gt, Montgomery limbs (:114-231)
 }
 
@@ -54,6 +54,15 @@ def main():
     for f, (per, names) in KATS.items():
         for n in names:
             kat["%s::%s" % (f, n)] = limbs(fn_body(os.path.join(REF, "src", f), n), per)
+    # scalar-field constants (src/scalar.rs:76-222, LARGEST :1051) and the byte encodings of test_to_bytes /
+    # test_from_bytes (:864-968): 32-byte decimal arrays in source order
+    sc = open(os.path.join(REF, "src/scalar.rs")).read()
+    for name in ["MODULUS", "GENERATOR", "R", "R2", "R3", "TWO_INV", "ROOT_OF_UNITY", "ROOT_OF_UNITY_INV", "DELTA", "LARGEST"]:
+        m = re.search(r"const %s: Scalar = Scalar\(\[(.*?)\]\);" % name, sc, re.S)
+        kat["scalar.rs::const_%s" % name] = limbs(m.group(1), 4)[0]
+    for fn in ["test_to_bytes", "test_from_bytes"]:
+        arrs = re.findall(r"\[\s*((?:\d+,\s*){31}\d+)\s*\]", fn_body(os.path.join(REF, "src/scalar.rs"), fn))
+        kat["scalar.rs::%s_bytes" % fn] = [[int(x) for x in a.replace("\n", " ").split(",")] for a in arrs]
     # RELIC-derived pairing KAT bytes (src/tests/mod.rs:78-231): the expected Gt as raw byte list
     # the same value as sent by the RELIC author, canonical (non-Montgomery) big-endian hex (src/tests/mod.rs:81-95)
     body = fn_body(os.path.join(REF, "src/tests/mod.rs"), "test_pairing_result_against_relic")
