@@ -26,6 +26,12 @@ SIGNATURES = {
     "b200_tower_op": [_vp, _i, _i, _vp, _vp, _vp, _sz],
     "b200_glv_decompose": [_vp, _vp, _sz, _vp, _vp],
     "b200_imad_peak": [_vp, _i, C.POINTER(C.c_double), C.POINTER(C.c_double)],
+    "b200_fr_op": [_vp, _i, _vp, _vp, _sz, _vp],
+    "b200_fr_to_bytes": [_vp, _vp, _sz, _vp],
+    "b200_fr_from_bytes": [_vp, _vp, _sz, _vp, _vp],
+    "b200_fr_ntt": [_vp, _vp, _i, _i, _i, _vp],
+    "b200_fr_op_dev": [_vp, _i, _vp, _vp, _sz, _vp],
+    "b200_fr_ntt_dev": [_vp, _vp, _i, _i, _i, _vp],
     "b200_miller_loop_batch": [_vp, _vp, _vp, _vp, _vp, _sz, _vp],
     "b200_final_exponentiation_batch": [_vp, _vp, _sz, _vp],
     "b200_pairing_batch": [_vp, _vp, _vp, _vp, _vp, _sz, _vp],

@@ -342,6 +342,7 @@ void b200_ctx_destroy(b200_ctx *ctx) {
   for (int i = 0; i < b200_ctx::N_SYNC_EVENTS; i++)
     if (ctx->ev_sync[i]) cudaEventDestroy(ctx->ev_sync[i]);
   if (ctx->inv_pow2) cudaFree(ctx->inv_pow2);
+  if (ctx->fr_state && ctx->fr_state_free) ctx->fr_state_free(ctx->fr_state);
   if (ctx->arena) cudaFree(ctx->arena);
   if (ctx->stage) cudaFree(ctx->stage);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);

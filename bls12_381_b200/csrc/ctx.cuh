@@ -50,6 +50,9 @@ struct b200_ctx {
   bool timing = false;
   std::vector<cudaEvent_t> ev_pool;       // 2 per record
   std::vector<const char *> ev_names;     // one per record
+  // scalar-field NTT tables of capi_fr.cu (twiddles + coset powers for the last log_n used); freed by ctx_destroy
+  void *fr_state = nullptr;
+  void (*fr_state_free)(void *) = nullptr;
 };
 
 namespace b200 {

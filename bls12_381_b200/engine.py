@@ -175,6 +175,49 @@ class Engine:
             out.append((-k1 if sg[i] & 1 else k1, -k2 if sg[i] & 2 else k2))
         return out
 
+    # ---------------------------------------------------------------- scalar field Fr + NTT
+    FR_OPS = dict(mul=0, add=1, sub=2, square=3, neg=4, invert=5, double=11)
+
+    def fr_op(self, op, a, b=None):
+        """element-wise Scalar arithmetic on Montgomery limbs (n,4) uint64 (src/scalar.rs:554-627, :341, :408, :249)"""
+        a = _np(a, np.uint64, 4)
+        b = None if b is None else _np(b, np.uint64, 4)
+        out = np.empty_like(a)
+        self._ck(self.lib.b200_fr_op(self.h, self.FR_OPS[op], _hp(a), _hp(b), a.shape[0], _hp(out)), "fr_op")
+        return out
+
+    def fr_to_bytes(self, a):
+        """Scalar::to_bytes for a batch -> (n,32) uint8 canonical little-endian (the scalars msm()/mul_batch() take)"""
+        a = _np(a, np.uint64, 4)
+        out = np.empty((a.shape[0], 32), np.uint8)
+        self._ck(self.lib.b200_fr_to_bytes(self.h, _hp(a), a.shape[0], _hp(out)), "fr_to_bytes")
+        return out
+
+    def fr_from_bytes(self, b):
+        """Scalar::from_bytes for a batch -> (limbs (n,4), ok (n,)); non-canonical encodings give ok = 0, limbs 0"""
+        b = _np(b, np.uint8, 32)
+        out = np.empty((b.shape[0], 4), np.uint64)
+        ok = np.empty(b.shape[0], np.uint8)
+        self._ck(self.lib.b200_fr_from_bytes(self.h, _hp(b), b.shape[0], _hp(out), _hp(ok)), "fr_from_bytes")
+        return out, ok
+
+    def fr_ntt(self, a, inverse=False, coset=False):
+        """NTT over Fr on n = 2^k Montgomery elements, natural order in/out (see include/bls12381_b200.h)"""
+        a = _np(a, np.uint64, 4)
+        n = a.shape[0]
+        log_n = n.bit_length() - 1
+        if n < 1 or n != 1 << log_n:
+            raise ValueError("fr_ntt: length must be a power of two")
+        out = np.empty_like(a)
+        self._ck(self.lib.b200_fr_ntt(self.h, _hp(a), log_n, int(inverse), int(coset), _hp(out)), "fr_ntt")
+        return out
+
+    def fr_op_dev(self, op, a, b, n, out):
+        self._ck(self.lib.b200_fr_op_dev(self.h, self.FR_OPS[op], _dp(a), _dp(b), n, _dp(out)), "fr_op_dev")
+
+    def fr_ntt_dev(self, a, log_n, out, inverse=False, coset=False):
+        self._ck(self.lib.b200_fr_ntt_dev(self.h, _dp(a), log_n, int(inverse), int(coset), _dp(out)), "fr_ntt_dev")
+
     # ---------------------------------------------------------------- (de)serialization (SURVEY §8f rows 1-2)
     def serialize(self, k, xy, inf=None, compressed=True):
         """G{k}Affine::to_compressed / to_uncompressed for a batch -> (n, 48k | 96k) uint8"""

@@ -176,6 +176,32 @@ int b200_fp12_product_dev(b200_ctx *ctx, const void *in, size_t n, void *out);
  * bit 1 = k2 < 0. */
 int b200_glv_decompose(b200_ctx *ctx, const b200_scalar *scalars, size_t n, uint8_t *k1k2, uint8_t *signs);
 
+/* ---- scalar field Fr: batched arithmetic and the NTT -------------------------------------
+ * Elements are b200_fr = Scalar([u64; 4]) (src/scalar.rs:24): little-endian limbs, Montgomery form R = 2^256,
+ * canonical (< q).  b200_fr_op: out[i] = a[i] (op) b[i]; op = B200_OP_MUL (src/scalar.rs:554), _ADD (:600), _SUB (:582),
+ * _SQUARE (:341), _NEG (:613), _INVERT (:408; 0 -> 0 where the reference returns CtOption::None), B200_OP_DOUBLE
+ * (:249); b is ignored (may be NULL) for the unary ops.
+ * b200_fr_to_bytes = Scalar::to_bytes (:284): canonical 32-byte little-endian integers — the b200_scalar the MSM and
+ * scalar-multiplication entry points consume.  b200_fr_from_bytes = Scalar::from_bytes (:256): ok[i] = 1 and the
+ * Montgomery limbs when the encoding is canonical, else ok[i] = 0 and zero limbs.
+ * b200_fr_ntt: the transform every FFT over this field is built on (the reference exports its parameters:
+ * ROOT_OF_UNITY :200, S = 32 :191, MULTIPLICATIVE_GENERATOR = 7 :100), n = 2^log_n, natural order in and out:
+ *   forward  out[k] = sum_j in[j] w^(jk),  w = ROOT_OF_UNITY^(2^(32 - log_n));
+ *   inverse  out[j] = n^-1 sum_k in[k] w^(-jk);
+ *   coset    forward first scales in[j] by g^j, inverse finally scales out[j] by g^-j (g = 7): evaluation on /
+ *            interpolation from the coset g<w>  (bellman EvaluationDomain::coset_fft / icoset_fft).
+ * 0 <= log_n <= 28.  `in` and `out` may be the same buffer.  The n/2-entry twiddle table (16 n bytes of device
+ * memory) is cached in the ctx per log_n. */
+typedef struct { uint64_t l[4]; } b200_fr;      /* 32 B  src/scalar.rs:24 */
+#define B200_OP_DOUBLE 11
+int b200_fr_op(b200_ctx *ctx, int op, const b200_fr *a, const b200_fr *b, size_t n, b200_fr *out);
+int b200_fr_to_bytes(b200_ctx *ctx, const b200_fr *a, size_t n, b200_scalar *out);
+int b200_fr_from_bytes(b200_ctx *ctx, const b200_scalar *in, size_t n, b200_fr *out, uint8_t *ok);
+int b200_fr_ntt(b200_ctx *ctx, const b200_fr *in, int log_n, int inverse, int coset, b200_fr *out);
+/* device-pointer variants (32-byte aligned device memory; run on the ctx stream, not synchronised) */
+int b200_fr_op_dev(b200_ctx *ctx, int op, const void *a, const void *b, size_t n, void *out);
+int b200_fr_ntt_dev(b200_ctx *ctx, const void *in, int log_n, int inverse, int coset, void *out);
+
 /* ---- measurement helper: dependent-free IMAD.WIDE.U32 stream on all SMs; returns achieved
  * 32x32+64 multiply-adds per second (the integer roofline denominator) ------------ */
 int b200_imad_peak(b200_ctx *ctx, int iters, double *imad_per_sec, double *ms);

@@ -9,7 +9,7 @@
 #include "glv.cuh"
 #include "pairing.cuh"
 #ifdef EMUL_WITH_FR
-#include "fr.cuh"
+#include "fr_ntt.cuh"
 #endif
 
 using namespace b200;
@@ -196,4 +196,63 @@ void emul_glv_decompose(const uint32_t *s, size_t n, uint32_t *out) {
     out[10 * i + 9] = g.neg2;
   }
 }
+
 }  // extern "C"
+#ifdef EMUL_WITH_FR
+namespace {
+// a kernel "launch" on the host: every (block, thread) in turn; blocks are spread over host threads.  Only valid for
+// kernels without intra-block cooperation (no __syncthreads / shared memory / shuffles) — all of fr_ntt.cuh.
+struct emul_launcher {
+  int threads = 1;
+  int launches = 0;
+  template <class K, class... A>
+  int operator()(K k, unsigned grid, unsigned block, A... a) {
+    launches++;
+    auto run = [=](unsigned b0, unsigned step) {
+      blockDim = emul_dim3{block, 1, 1};
+      gridDim = emul_dim3{grid, 1, 1};
+      for (unsigned b = b0; b < grid; b += step) {
+        blockIdx = emul_dim3{b, 0, 0};
+        for (unsigned t = 0; t < block; t++) {
+          threadIdx = emul_dim3{t, 0, 0};
+          k(a...);
+        }
+      }
+    };
+    if (threads <= 1 || grid < 2) {
+      run(0, 1);
+    } else {
+      std::vector<std::thread> th;
+      for (int t = 0; t < threads; t++) th.emplace_back(run, (unsigned)t, (unsigned)threads);
+      for (auto &x : th) x.join();
+    }
+    return 0;
+  }
+};
+}  // namespace
+extern "C" {
+int emul_fr_op(int op, const char *a, const char *b, char *out, size_t n) {
+  emul_launcher l;
+  return l(k_fr_op, (unsigned)((n + 255) / 256), 256u, op, a, b, out, n);
+}
+int emul_fr_to_bytes(const char *a, char *out, size_t n) {
+  emul_launcher l;
+  return l(k_fr_to_bytes, (unsigned)((n + 255) / 256), 256u, a, out, n);
+}
+int emul_fr_from_bytes(const char *in, char *out, uint8_t *ok, size_t n) {
+  emul_launcher l;
+  return l(k_fr_from_bytes, (unsigned)((n + 255) / 256), 256u, in, out, ok, n);
+}
+// the full launch sequence of b200_fr_ntt (tables + passes); returns the number of pass launches
+int emul_fr_ntt(const char *in, int log_n, int inverse, int coset, char *out, int threads) {
+  emul_launcher l;
+  l.threads = threads;
+  std::vector<char> mem(fr_tables_bytes(log_n) + 256);
+  char *base = mem.data() + ((256 - ((uintptr_t)mem.data() & 255)) & 255);
+  fr_ntt_tables tb{};
+  int rc = fr_ntt_build_tables(l, base, log_n, &tb);
+  if (rc < 0) return rc;
+  return fr_ntt_run(l, in, out, log_n, inverse != 0, coset != 0, tb);
+}
+}  // extern "C"
+#endif
