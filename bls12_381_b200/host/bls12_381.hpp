@@ -54,6 +54,45 @@ struct Scalar {
   b200_scalar bytes;  // == Scalar::to_bytes(): canonical little-endian, < q   (src/scalar.rs:284)
 };
 
+// An element of the scalar field in the reference's in-memory form, Scalar([u64; 4]) Montgomery limbs (src/scalar.rs:24),
+// with the batched operators of the GPU path.  Fr::to_bytes gives the `Scalar` above (what msm / mul_batch consume).
+struct Fr {
+  b200_fr v;
+
+  static std::vector<Fr> op(const Engine &e, int opcode, const std::vector<Fr> &a, const std::vector<Fr> *b) {
+    if (b && b->size() != a.size()) throw Error(B200_EINVAL, "Fr: length mismatch");
+    std::vector<Fr> out(a.size());
+    e.check(b200_fr_op(e.raw(), opcode, &a.data()->v, b ? &b->data()->v : nullptr, a.size(), &out.data()->v), "fr_op");
+    return out;
+  }
+  static std::vector<Fr> mul(const Engine &e, const std::vector<Fr> &a, const std::vector<Fr> &b) { return op(e, B200_OP_MUL, a, &b); }
+  static std::vector<Fr> add(const Engine &e, const std::vector<Fr> &a, const std::vector<Fr> &b) { return op(e, B200_OP_ADD, a, &b); }
+  static std::vector<Fr> sub(const Engine &e, const std::vector<Fr> &a, const std::vector<Fr> &b) { return op(e, B200_OP_SUB, a, &b); }
+  static std::vector<Fr> square(const Engine &e, const std::vector<Fr> &a) { return op(e, B200_OP_SQUARE, a, nullptr); }
+  static std::vector<Fr> neg(const Engine &e, const std::vector<Fr> &a) { return op(e, B200_OP_NEG, a, nullptr); }
+  static std::vector<Fr> invert(const Engine &e, const std::vector<Fr> &a) { return op(e, B200_OP_INVERT, a, nullptr); }  // 0 -> 0
+  static std::vector<Scalar> to_bytes(const Engine &e, const std::vector<Fr> &a) {  // src/scalar.rs:284
+    std::vector<Scalar> out(a.size());
+    e.check(b200_fr_to_bytes(e.raw(), &a.data()->v, a.size(), &out.data()->bytes), "fr_to_bytes");
+    return out;
+  }
+  // src/scalar.rs:256: ok[i] = 0 for a non-canonical encoding (the reference's CtOption::None)
+  static std::vector<Fr> from_bytes(const Engine &e, const std::vector<Scalar> &in, std::vector<uint8_t> &ok) {
+    std::vector<Fr> out(in.size());
+    ok.resize(in.size());
+    e.check(b200_fr_from_bytes(e.raw(), &in.data()->bytes, in.size(), &out.data()->v, ok.data()), "fr_from_bytes");
+    return out;
+  }
+  // in-place transform of a.size() = 2^k elements over Scalar::ROOT_OF_UNITY (src/scalar.rs:200); throws EINVAL otherwise
+  static void ntt(const Engine &e, std::vector<Fr> &a, bool inverse = false, bool coset = false) {
+    size_t n = a.size();
+    int k = 0;
+    while (((size_t)1 << k) < n) k++;
+    if (n == 0 || ((size_t)1 << k) != n) throw Error(B200_EINVAL, "Fr::ntt: length must be a power of two");
+    e.check(b200_fr_ntt(e.raw(), &a.data()->v, k, inverse, coset, &a.data()->v), "fr_ntt");
+  }
+};
+
 struct G1Affine {
   b200_g1_affine xy;
   uint8_t infinity;  // Choice; identity() is (0, 1, infinity = 1)   (src/g1.rs:187-193)

@@ -14,6 +14,10 @@ SRC = r'''
 using namespace bls12_381;
 int main() {
   static_assert(sizeof(G1Affine) == 97 || sizeof(G1Affine) == 104, "G1Affine = coords + flag");
+  static_assert(sizeof(Fr) == 32 && sizeof(Scalar) == 32, "Fr = Scalar([u64; 4]), Scalar = to_bytes()");
+  using NttFn = void (*)(const Engine &, std::vector<Fr> &, bool, bool);
+  NttFn ntt_fn = &Fr::ntt;            // the scalar-field surface instantiates against the C ABI
+  (void)ntt_fn;
   try {
     Engine e(0);
     std::vector<G1Projective> p(2);
