@@ -5,6 +5,7 @@
 #include <thread>
 
 #include "bls12_381_oracle.hpp"
+#include "h2c_oracle.hpp"
 
 using namespace bls_oracle;
 
@@ -297,6 +298,80 @@ void orc_fr_ntt(const uint64_t *a, int log_n, int inverse, int coset, uint64_t *
     }
   }
   std::memcpy(out, x.data(), 32 * n);
+}
+
+// ---------------------------------------------------------------- hash to curve
+int orc_expand_message_xmd_sha256(const uint8_t *msg, size_t msg_len, const uint8_t *dst, size_t dst_len, size_t len_in_bytes,
+                                  uint8_t *out) {
+  return expand_message_xmd_sha256(msg, msg_len, dst, dst_len, len_in_bytes, out) ? 0 : -1;
+}
+void orc_sha256(const uint8_t *msg, size_t n, uint8_t *out) {
+  Sha256 h;
+  h.update(msg, n);
+  h.finish(out);
+}
+// msgs: concatenated messages, message i = msgs[off[i] .. off[i+1]); out: n projective points
+int orc_g1_hash(const uint8_t *msgs, const uint64_t *off, size_t n, const uint8_t *dst, size_t dst_len, int encode, uint64_t *out,
+                int threads) {
+  std::atomic<int> bad{0};
+  parallel_for(n, threads, [&](size_t i) {
+    G1Projective r{};
+    if (!g1_hash(msgs + off[i], (size_t)(off[i + 1] - off[i]), dst, dst_len, encode != 0, r)) bad = 1;
+    std::memcpy(out + 18 * i, &r, 144);
+  });
+  return bad ? -1 : 0;
+}
+int orc_g2_hash(const uint8_t *msgs, const uint64_t *off, size_t n, const uint8_t *dst, size_t dst_len, int encode, uint64_t *out,
+                int threads) {
+  std::atomic<int> bad{0};
+  parallel_for(n, threads, [&](size_t i) {
+    G2Projective r{};
+    if (!g2_hash(msgs + off[i], (size_t)(off[i + 1] - off[i]), dst, dst_len, encode != 0, r)) bad = 1;
+    std::memcpy(out + 36 * i, &r, 288);
+  });
+  return bad ? -1 : 0;
+}
+// the stages on their own.  kind: 0 g1 sswu (Fp -> E' point), 1 g1 iso_map, 2 g1 map_to_curve (Fp -> E), 3 g1
+// clear_cofactor, 4..7 the same for g2 (Fp2).  in: n field elements or n projective points; out: n projective points
+int orc_h2c_stage(int kind, const uint64_t *in, uint64_t *out, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    if (kind < 4) {
+      G1Projective r{}, p{};
+      Fp u{};
+      if (kind == 0 || kind == 2) std::memcpy(&u, in + 6 * i, 48); else std::memcpy(&p, in + 18 * i, 144);
+      r = kind == 0 ? g1_map_to_curve_simple_swu(u) : kind == 1 ? g1_iso_map(p) : kind == 2 ? g1_map_to_curve(u) : g1p_clear_cofactor(p);
+      std::memcpy(out + 18 * i, &r, 144);
+    } else if (kind < 8) {
+      G2Projective r{}, p{};
+      Fp2 u{};
+      if (kind == 4 || kind == 6) std::memcpy(&u, in + 12 * i, 96); else std::memcpy(&p, in + 36 * i, 288);
+      r = kind == 4 ? g2_map_to_curve_simple_swu(u) : kind == 5 ? g2_iso_map(p) : kind == 6 ? g2_map_to_curve(u) : g2p_clear_cofactor(p);
+      std::memcpy(out + 36 * i, &r, 288);
+    } else {
+      return -1;
+    }
+  }
+  return 0;
+}
+// hash_to_field: 64 uniform bytes per Fp (src/hash_to_curve/map_g1.rs:513) ; sgn0 (:535, map_g2.rs:382)
+void orc_fp_from_okm(const uint8_t *okm, uint64_t *out, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    Fp r = fp_from_okm(okm + 64 * i);
+    std::memcpy(out + 6 * i, &r, 48);
+  }
+}
+void orc_sgn0(int level, const uint64_t *a, uint8_t *out, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    if (level == 1) {
+      Fp x{};
+      std::memcpy(&x, a + 6 * i, 48);
+      out[i] = fp_sgn0(x);
+    } else {
+      Fp2 x{};
+      std::memcpy(&x, a + 12 * i, 96);
+      out[i] = fp2_sgn0(x);
+    }
+  }
 }
 
 // ---------------------------------------------------------------- G1

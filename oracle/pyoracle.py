@@ -19,7 +19,7 @@ _SO = os.path.join(_DIR, "liboracle.so")
 
 
 def build(force=False):
-    src = [os.path.join(_DIR, f) for f in ("oracle_capi.cpp", "bls12_381_oracle.hpp")]
+    src = [os.path.join(_DIR, f) for f in ("oracle_capi.cpp", "bls12_381_oracle.hpp", "h2c_oracle.hpp", "h2c_constants.inc")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
         subprocess.check_call(["make", "-C", _DIR, "-s", "liboracle.so"])
     return _SO
@@ -176,6 +176,72 @@ def fr_ntt(a, inverse=False, coset=False, threads=1):
     assert a.shape[0] == 1 << log_n
     out = np.empty_like(a)
     lib().orc_fr_ntt(_p(a), log_n, int(inverse), int(coset), _p(out), threads)
+    return out
+
+
+# ---------------------------------------------------------------- hash to curve (src/hash_to_curve/)
+def expand_message_xmd(msg, dst, len_in_bytes):
+    msg, dst = _u8(np.frombuffer(bytes(msg), np.uint8)), _u8(np.frombuffer(bytes(dst), np.uint8))
+    out = np.empty(len_in_bytes, np.uint8)
+    rc = lib().orc_expand_message_xmd_sha256(_p(msg), C.c_size_t(msg.size), _p(dst), C.c_size_t(dst.size),
+                                             C.c_size_t(len_in_bytes), _p(out))
+    if rc != 0:
+        raise ValueError("expand_message_xmd: ell > 255 or len_in_bytes > 65535")
+    return out
+
+
+def sha256(msg):
+    msg = _u8(np.frombuffer(bytes(msg), np.uint8))
+    out = np.empty(32, np.uint8)
+    lib().orc_sha256(_p(msg), C.c_size_t(msg.size), _p(out))
+    return out.tobytes()
+
+
+def pack_messages(msgs):
+    """list of bytes -> (concatenated uint8 array, offsets uint64 (n+1,))"""
+    off = np.zeros(len(msgs) + 1, np.uint64)
+    off[1:] = np.cumsum([len(m) for m in msgs])
+    cat = np.frombuffer(b"".join(bytes(m) for m in msgs) or b"\0", np.uint8).copy()
+    return cat, off
+
+
+def hash_to_curve(k, msgs, dst, encode=False, threads=1):
+    """HashToCurve<ExpandMsgXmd<Sha256>>::hash_to_curve / encode_to_curve for G{k} -> (n, 18k) projective"""
+    cat, off = pack_messages(msgs)
+    dst = _u8(np.frombuffer(bytes(dst), np.uint8))
+    out = np.empty((len(msgs), 18 * k), np.uint64)
+    rc = getattr(lib(), "orc_g%d_hash" % k)(_p(cat), _p(off), C.c_size_t(len(msgs)), _p(dst), C.c_size_t(dst.size),
+                                            int(encode), _p(out), threads)
+    assert rc == 0
+    return out
+
+
+H2C_STAGE = dict(g1_sswu=0, g1_iso_map=1, g1_map_to_curve=2, g1_clear_cofactor=3, g2_sswu=4, g2_iso_map=5,
+                 g2_map_to_curve=6, g2_clear_cofactor=7)
+
+
+def h2c_stage(name, a):
+    kind = H2C_STAGE[name]
+    k = 1 if kind < 4 else 2
+    win = 6 * k if kind % 4 in (0, 2) else 18 * k
+    a = _u64(a, win)
+    out = np.empty((a.shape[0], 18 * k), np.uint64)
+    rc = lib().orc_h2c_stage(kind, _p(a), _p(out), C.c_size_t(a.shape[0]))
+    assert rc == 0
+    return out
+
+
+def fp_from_okm(okm):
+    okm = _u8(okm, 64)
+    out = np.empty((okm.shape[0], 6), np.uint64)
+    lib().orc_fp_from_okm(_p(okm), _p(out), C.c_size_t(okm.shape[0]))
+    return out
+
+
+def sgn0(level, a):
+    a = _u64(a, 6 * level)
+    out = np.empty(a.shape[0], np.uint8)
+    lib().orc_sgn0(level, _p(a), _p(out), C.c_size_t(a.shape[0]))
     return out
 
 

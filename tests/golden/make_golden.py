@@ -42,11 +42,51 @@ KATS = {
     "fp6.rs": (6, ["test_arithmetic"]),
     "fp12.rs": (6, ["test_arithmetic"]),
     "g1.rs": (6, ["test_doubling", "test_projective_addition", "test_mixed_addition", "test_beta", "test_is_torsion_free"]),
+    "hash_to_curve/map_g1.rs": (6, ["test_simple_swu_expected"]),
     "g2.rs": (6, ["test_doubling", "test_projective_addition", "test_mixed_addition", "test_is_torsion_free"]),
     "pairings.rs": (6, ["generator"]),           # Gt::generator(), src/pairings.rs:359-475
     "scalar.rs": (4, ["test_from_bytes_wide_maximum", "test_addition", "test_double"]),
     "tests/mod.rs": (6, ["test_pairing_result_against_relic"]),   # expected Gt, Montgomery limbs (:114-231)
 }
+
+
+def rust_bytes(lit):
+    """body of a Rust b"..." literal -> bytes (handles the backslash-newline continuation and \\x escapes)"""
+    lit = re.sub(r"\\\n\s*", "", lit)
+    return lit.encode("latin1").decode("unicode_escape").encode("latin1")
+
+
+def h2c_vectors():
+    """RFC 9380 (draft-16) vectors the reference's integration tests hold: tests/expand_msg.rs (XMD SHA-256, short and
+    long DST), tests/hash_to_curve_g1.rs, tests/hash_to_curve_g2.rs.  Everything as hex strings."""
+    out = {}
+    src = open(os.path.join(REF, "tests/expand_msg.rs")).read()
+    for fn in ["expand_msg_xmd_works_for_draft16_testvectors_sha256", "expand_msg_xmd_works_for_draft16_testvectors_sha256_long_dst"]:
+        body = fn_body(os.path.join(REF, "tests/expand_msg.rs"), fn)
+        dst = rust_bytes(re.search(r'let dst = b"(.*?)";', body, re.S).group(1))
+        cases = []
+        for m in re.finditer(r'msg: b"(.*?)",\s*dst,\s*len_in_bytes: (0x[0-9a-f]+),\s*uniform_bytes: &hex!\(\s*"(.*?)"\s*\)', body, re.S):
+            cases.append({"msg": rust_bytes(m.group(1)).hex(), "len_in_bytes": int(m.group(2), 16),
+                          "uniform_bytes": re.sub(r"\s+", "", m.group(3))})
+        assert len(cases) == 10, (fn, len(cases))
+        out["expand_msg.rs::" + fn] = {"dst": dst.hex(), "cases": cases}
+    for f, fns in (("hash_to_curve_g1.rs", ["encode_to_curve_works_for_draft16_testvectors_g1_sha256_nu",
+                                            "hash_to_curve_works_for_draft16_testvectors_g1_sha256_ro"]),
+                   ("hash_to_curve_g2.rs", ["encode_to_curve_works_for_draft16_testvectors_g2_sha256_nu",
+                                            "hash_to_curve_works_for_draft16_testvectors_g2_sha256_ro"])):
+        for fn in fns:
+            body = fn_body(os.path.join(REF, "tests", f), fn)
+            dst = rust_bytes(re.search(r'let dst = b"(.*?)";', body, re.S).group(1))
+            cases = []
+            for m in re.finditer(r'msg: b"(.*?)",\s*dst,\s*expected: &hex!\(\s*"(.*?)"\s*\)', body, re.S):
+                cases.append({"msg": rust_bytes(m.group(1)).hex(), "expected": re.sub(r"\s+", "", m.group(2))})
+            assert len(cases) == 5, (fn, len(cases))
+            out[f + "::" + fn] = {"dst": dst.hex(), "cases": cases}
+    # src/hash_to_curve/map_scalar.rs:25-45 (hash_to_field for Scalar)
+    body = fn_body(os.path.join(REF, "src/hash_to_curve/map_scalar.rs"), "test_hash_to_scalar")
+    out["map_scalar.rs::test_hash_to_scalar"] = [
+        {"okm": rust_bytes(a).hex(), "expected": b} for a, b in re.findall(r'b"(.*?)",\s*"0x([0-9a-f]{64})"', body, re.S)]
+    return out
 
 
 def main():
@@ -70,6 +110,7 @@ def main():
     assert len(words) == 72
     kat["tests/mod.rs::relic_canonical_hex"] = ["".join(words[i:i + 6]) for i in range(0, 72, 6)]
     json.dump(kat, open(os.path.join(HERE, "kat.json"), "w"), indent=0)
+    json.dump(h2c_vectors(), open(os.path.join(HERE, "h2c_vectors.json"), "w"), indent=0)
     d = {}
     for name in ["g1_compressed", "g1_uncompressed", "g2_compressed", "g2_uncompressed"]:
         d[name] = np.fromfile(os.path.join(REF, "src/tests/%s_valid_test_vectors.dat" % name), dtype=np.uint8)
