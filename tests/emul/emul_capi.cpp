@@ -10,6 +10,7 @@
 #include "pairing.cuh"
 #ifdef EMUL_WITH_FR
 #include "fr_ntt.cuh"
+#include "h2c.cuh"
 #endif
 
 using namespace b200;
@@ -242,6 +243,29 @@ int emul_fr_to_bytes(const char *a, char *out, size_t n) {
 int emul_fr_from_bytes(const char *in, char *out, uint8_t *ok, size_t n) {
   emul_launcher l;
   return l(k_fr_from_bytes, (unsigned)((n + 255) / 256), 256u, in, out, ok, n);
+}
+// hash to curve: the launch sequence of b200_g{1,2}_hash_to_curve
+int emul_h2c_expand(const uint8_t *msgs, const uint64_t *off, size_t n, const uint8_t *dst, size_t dst_len, uint32_t len_in_bytes,
+                    uint8_t *out) {
+  uint8_t dp[256];
+  int dpl = h2c_dst_prime(dst, dst_len, dp);
+  emul_launcher l;
+  return l(k_h2c_expand, (unsigned)((n + 127) / 128), 128u, msgs, off, n, (const uint8_t *)dp, dpl, len_in_bytes, out);
+}
+int emul_h2c_hash(int group, const uint8_t *msgs, const uint64_t *off, size_t n, const uint8_t *dst, size_t dst_len, int encode,
+                  char *out, int threads) {
+  uint8_t dp[256];
+  int dpl = h2c_dst_prime(dst, dst_len, dp);
+  const int count = encode ? 1 : 2;
+  std::vector<uint8_t> okm((size_t)h2c_okm_bytes(group, count) * n + 1);
+  emul_launcher l;
+  l.threads = threads;
+  return h2c_hash_run(l, group, msgs, off, n, (const uint8_t *)dp, dpl, count, okm.data(), out);
+}
+int emul_h2c_stage(int group, int kind, const char *in, size_t n, char *out) {
+  emul_launcher l;
+  if (group == 1) return l(k_h2c_stage<fp>, (unsigned)((n + 127) / 128), 128u, kind, in, n, out);
+  return l(k_h2c_stage<fp2>, (unsigned)((n + 127) / 128), 128u, kind, in, n, out);
 }
 // the full launch sequence of b200_fr_ntt (tables + passes); returns the number of pass launches
 int emul_fr_ntt(const char *in, int log_n, int inverse, int coset, char *out, int threads) {
