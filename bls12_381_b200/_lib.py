@@ -32,6 +32,10 @@ SIGNATURES = {
     "b200_fr_ntt": [_vp, _vp, _i, _i, _i, _vp],
     "b200_fr_op_dev": [_vp, _i, _vp, _vp, _sz, _vp],
     "b200_fr_ntt_dev": [_vp, _vp, _i, _i, _i, _vp],
+    "b200_expand_message_xmd_sha256": [_vp, _vp, _vp, _sz, _vp, _sz, _sz, _vp],
+    "b200_g1_hash_to_curve": [_vp, _vp, _vp, _sz, _vp, _sz, _i, _vp],
+    "b200_g2_hash_to_curve": [_vp, _vp, _vp, _sz, _vp, _sz, _i, _vp],
+    "b200_h2c_stage": [_vp, _i, _i, _vp, _sz, _vp],
     "b200_miller_loop_batch": [_vp, _vp, _vp, _vp, _vp, _sz, _vp],
     "b200_final_exponentiation_batch": [_vp, _vp, _sz, _vp],
     "b200_pairing_batch": [_vp, _vp, _vp, _vp, _vp, _sz, _vp],

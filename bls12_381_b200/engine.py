@@ -218,6 +218,43 @@ class Engine:
     def fr_ntt_dev(self, a, log_n, out, inverse=False, coset=False):
         self._ck(self.lib.b200_fr_ntt_dev(self.h, _dp(a), log_n, int(inverse), int(coset), _dp(out)), "fr_ntt_dev")
 
+    # ---------------------------------------------------------------- hash to curve
+    @staticmethod
+    def _pack(msgs):
+        off = np.zeros(len(msgs) + 1, np.uint64)
+        if len(msgs):
+            off[1:] = np.cumsum([len(m) for m in msgs])
+        cat = np.frombuffer(b"".join(bytes(m) for m in msgs) or b"\0", np.uint8).copy()
+        return cat, off
+
+    def expand_message_xmd(self, msgs, dst, len_in_bytes):
+        """ExpandMsgXmd<Sha256> for a list of byte strings -> (n, len_in_bytes) uint8 (src/hash_to_curve/expand_msg.rs:230)"""
+        cat, off = self._pack(msgs)
+        d = np.frombuffer(bytes(dst) or b"\0", np.uint8).copy()
+        out = np.empty((len(msgs), len_in_bytes), np.uint8)
+        self._ck(self.lib.b200_expand_message_xmd_sha256(self.h, _hp(cat), _hp(off), len(msgs), _hp(d), len(dst), len_in_bytes,
+                                                         _hp(out)), "expand_message_xmd")
+        return out
+
+    def hash_to_curve(self, k, msgs, dst, encode=False):
+        """HashToCurve<ExpandMsgXmd<Sha256>>::hash_to_curve (encode=False) / encode_to_curve for G{k}: list of byte
+        strings -> (n, 18k) projective limbs (src/hash_to_curve/mod.rs:86-108)"""
+        cat, off = self._pack(msgs)
+        d = np.frombuffer(bytes(dst) or b"\0", np.uint8).copy()
+        out = np.empty((len(msgs), self.PROJ[k]), np.uint64)
+        self._ck(getattr(self.lib, self._g(k) + "hash_to_curve")(self.h, _hp(cat), _hp(off), len(msgs), _hp(d), len(dst),
+                                                                  int(encode), _hp(out)), "hash_to_curve")
+        return out
+
+    H2C_KIND = dict(sswu=0, iso_map=1, map_to_curve=2, clear_cofactor=3)
+
+    def h2c_stage(self, k, kind, a):
+        kind = self.H2C_KIND[kind]
+        a = _np(a, np.uint64, 6 * k if kind in (0, 2) else self.PROJ[k])
+        out = np.empty((a.shape[0], self.PROJ[k]), np.uint64)
+        self._ck(self.lib.b200_h2c_stage(self.h, k, kind, _hp(a), a.shape[0], _hp(out)), "h2c_stage")
+        return out
+
     # ---------------------------------------------------------------- (de)serialization (SURVEY §8f rows 1-2)
     def serialize(self, k, xy, inf=None, compressed=True):
         """G{k}Affine::to_compressed / to_uncompressed for a batch -> (n, 48k | 96k) uint8"""

@@ -166,6 +166,38 @@ struct G2Projective {
   }
 };
 
+// <G{1,2}Projective as HashToCurve<ExpandMsgXmd<Sha256>>>::hash_to_curve / encode_to_curve for a batch of messages
+// (src/hash_to_curve/mod.rs:86-108); `dst` is the domain separation tag shared by the batch
+namespace detail {
+inline void pack(const std::vector<std::string> &msgs, std::vector<uint8_t> &cat, std::vector<uint64_t> &off) {
+  off.assign(1, 0);
+  for (const auto &m : msgs) {
+    cat.insert(cat.end(), m.begin(), m.end());
+    off.push_back(cat.size());
+  }
+}
+}  // namespace detail
+inline std::vector<G1Projective> hash_to_curve_g1(const Engine &e, const std::vector<std::string> &msgs, const std::string &dst,
+                                                  bool encode = false) {
+  std::vector<uint8_t> cat;
+  std::vector<uint64_t> off;
+  detail::pack(msgs, cat, off);
+  std::vector<G1Projective> out(msgs.size());
+  e.check(b200_g1_hash_to_curve(e.raw(), cat.data(), off.data(), msgs.size(), (const uint8_t *)dst.data(), dst.size(), encode,
+                                &out.data()->v), "g1_hash_to_curve");
+  return out;
+}
+inline std::vector<G2Projective> hash_to_curve_g2(const Engine &e, const std::vector<std::string> &msgs, const std::string &dst,
+                                                  bool encode = false) {
+  std::vector<uint8_t> cat;
+  std::vector<uint64_t> off;
+  detail::pack(msgs, cat, off);
+  std::vector<G2Projective> out(msgs.size());
+  e.check(b200_g2_hash_to_curve(e.raw(), cat.data(), off.data(), msgs.size(), (const uint8_t *)dst.data(), dst.size(), encode,
+                                &out.data()->v), "g2_hash_to_curve");
+  return out;
+}
+
 struct Gt {
   b200_fp12 v;  // canonical Fp12 (src/pairings.rs:211)
 };

@@ -202,6 +202,24 @@ int b200_fr_ntt(b200_ctx *ctx, const b200_fr *in, int log_n, int inverse, int co
 int b200_fr_op_dev(b200_ctx *ctx, int op, const void *a, const void *b, size_t n, void *out);
 int b200_fr_ntt_dev(b200_ctx *ctx, const void *in, int log_n, int inverse, int coset, void *out);
 
+/* ---- batched hash to curve: the RFC 9380 suites BLS12381G1_XMD:SHA-256_SSWU_{RO,NU}_ and
+ * BLS12381G2_XMD:SHA-256_SSWU_{RO,NU}_, i.e. <G1Projective as HashToCurve<ExpandMsgXmd<Sha256>>>::hash_to_curve /
+ * encode_to_curve (src/hash_to_curve/mod.rs:86-92, :103-108) and the G2 equivalents.
+ * Messages are passed concatenated: message i = msgs[offsets[i] .. offsets[i+1]) (offsets has n + 1 entries, ascending,
+ * offsets[0] may be non-zero); the domain separation tag `dst` is shared by the batch (longer than 255 bytes: reduced
+ * as RFC 9380 5.3.3 / src/hash_to_curve/expand_msg.rs:64-84).  encode = 0: hash_to_curve (random oracle, two field
+ * elements), 1: encode_to_curve (non-uniform, one).  out[i] = the projective point, limb-identical to the reference's.
+ * b200_expand_message_xmd_sha256: out[i * len_in_bytes ..] = expand_message_xmd(msg_i, dst, len_in_bytes)
+ * (src/hash_to_curve/expand_msg.rs:230-300); B200_EINVAL where the reference panics (ceil(len/32) > 255).
+ * b200_h2c_stage: the steps on their own (parity surface).  group 1 / 2; kind 0 map_to_curve_simple_swu (field element ->
+ * point of the isogenous curve, src/hash_to_curve/map_g1.rs:550 / map_g2.rs:391), 1 iso_map (:589 / :457), 2 map_to_curve
+ * (:635 / :497), 3 clear_cofactor (src/g1.rs:800, src/g2.rs:938); in: n field elements (kind 0, 2) or n projective
+ * points (kind 1, 3); out: n projective points. */
+int b200_expand_message_xmd_sha256(b200_ctx *ctx, const uint8_t *msgs, const uint64_t *offsets, size_t n, const uint8_t *dst, size_t dst_len, size_t len_in_bytes, uint8_t *out);
+int b200_g1_hash_to_curve(b200_ctx *ctx, const uint8_t *msgs, const uint64_t *offsets, size_t n, const uint8_t *dst, size_t dst_len, int encode, b200_g1_projective *out);
+int b200_g2_hash_to_curve(b200_ctx *ctx, const uint8_t *msgs, const uint64_t *offsets, size_t n, const uint8_t *dst, size_t dst_len, int encode, b200_g2_projective *out);
+int b200_h2c_stage(b200_ctx *ctx, int group, int kind, const void *in, size_t n, void *out);
+
 /* ---- measurement helper: dependent-free IMAD.WIDE.U32 stream on all SMs; returns achieved
  * 32x32+64 multiply-adds per second (the integer roofline denominator) ------------ */
 int b200_imad_peak(b200_ctx *ctx, int iters, double *imad_per_sec, double *ms);

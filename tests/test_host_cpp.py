@@ -18,6 +18,8 @@ int main() {
   using NttFn = void (*)(const Engine &, std::vector<Fr> &, bool, bool);
   NttFn ntt_fn = &Fr::ntt;            // the scalar-field surface instantiates against the C ABI
   (void)ntt_fn;
+  auto h2c_fn = &hash_to_curve_g2;   // hash-to-curve surface
+  (void)h2c_fn;
   try {
     Engine e(0);
     std::vector<G1Projective> p(2);
