@@ -1,5 +1,7 @@
 // C ABI, part 5: scalar-field (Fr) batch arithmetic and the NTT.  Kernels and the launch
 // plan live in fr_ntt.cuh (shared with the CPU test harness); this file owns the device memory and the streams.
+#include <new>
+
 #include "ctx.cuh"
 #include "fr_ntt.cuh"
 

@@ -1,5 +1,7 @@
 // C ABI, part 6: batched hash to curve.  Device functions, kernels and the launch plan live in
 // h2c.cuh (shared with the CPU test harness); this file stages the buffers.
+#include <vector>
+
 #include "ctx.cuh"
 #include "h2c.cuh"
 
