@@ -26,7 +26,7 @@ struct gpu_launcher {
   template <class K, class... A>
   int operator()(K k, unsigned grid, unsigned block, A... a) {
     int tr = timing_begin(ctx, "k_fr");
-    k<<<grid, block, 0, ctx->stream>>>(a...);
+    B200_KERNEL_LAUNCH(k, grid, block, 0, ctx->stream, a...);
     timing_end(ctx, tr);
     ctx->launches++;
     cudaError_t e = cudaGetLastError();

@@ -126,10 +126,18 @@ inline void timing_end(b200_ctx *ctx, int r, cudaStream_t strm = nullptr) {
   if (r >= 0) cudaEventRecord(ctx->ev_pool[2 * r + 1], strm ? strm : ctx->stream);
 }
 
+// the one place a kernel is launched from.  The CPU test harness (tests/emul/, B200_HOST_EMUL) compiles the host side of
+// the units with non-cooperative kernels against a mock runtime and turns a launch into a (block, thread) loop.
+#ifdef B200_HOST_EMUL
+#define B200_KERNEL_LAUNCH(kernel, grid, block, smem, strm, ...) emul_kernel_launch(kernel, grid, block, __VA_ARGS__)
+#else
+#define B200_KERNEL_LAUNCH(kernel, grid, block, smem, strm, ...) kernel<<<(grid), (block), (smem), (strm)>>>(__VA_ARGS__)
+#endif
+
 #define B200_LAUNCH(ctx, kernel, grid, block, smem, ...)                                 \
   do {                                                                                   \
     int tr__ = b200::timing_begin(ctx, #kernel);                                         \
-    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                     \
+    B200_KERNEL_LAUNCH(kernel, grid, block, smem, (ctx)->stream, __VA_ARGS__);           \
     b200::timing_end(ctx, tr__);                                                         \
     (ctx)->launches++;                                                                   \
     cudaError_t e__ = cudaGetLastError();                                                \
@@ -140,7 +148,7 @@ inline void timing_end(b200_ctx *ctx, int r, cudaStream_t strm = nullptr) {
 #define B200_LAUNCH_ON(ctx, strm, kernel, grid, block, smem, ...)                        \
   do {                                                                                   \
     int tr__ = b200::timing_begin(ctx, #kernel, strm);                                   \
-    kernel<<<(grid), (block), (smem), (strm)>>>(__VA_ARGS__);                            \
+    B200_KERNEL_LAUNCH(kernel, grid, block, smem, strm, __VA_ARGS__);                    \
     b200::timing_end(ctx, tr__, strm);                                                   \
     (ctx)->launches++;                                                                   \
     cudaError_t e__ = cudaGetLastError();                                                \

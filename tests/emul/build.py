@@ -12,7 +12,7 @@ def _digest(extra):
     h = hashlib.sha256(extra.encode())
     for d in (_DIR, _CSRC):
         for f in sorted(os.listdir(d)):
-            if f.endswith((".cuh", ".h", ".cpp", ".inc")):
+            if f.endswith((".cuh", ".h", ".cpp", ".inc", ".cu")):
                 h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()
 
@@ -30,5 +30,24 @@ def build(variant="default"):
     cmd = ["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-pthread", "-Wno-unknown-pragmas", "-I", _DIR, "-I", _CSRC,
            "-I", os.path.join(_ROOT, "include")] + flags + [os.path.join(_DIR, "emul_capi.cpp"), "-o", so]
     subprocess.check_call(cmd)
+    open(stamp, "w").write(dg)
+    return so
+
+
+def build_cabi():
+    """the host side of capi_fr.cu / capi_h2c.cu against the mock CUDA runtime (tests/emul/mock) -> libemul_cabi.so"""
+    so = os.path.join(_DIR, "libemul_cabi.so")
+    stamp = so + ".stamp"
+    dg = _digest("cabi")
+    if os.path.exists(so) and os.path.exists(stamp) and open(stamp).read() == dg:
+        return so
+    common = ["g++", "-O1", "-std=c++17", "-fPIC", "-pthread", "-Wno-unknown-pragmas", "-I", os.path.join(_DIR, "mock"), "-I", _DIR,
+              "-I", _CSRC, "-I", os.path.join(_ROOT, "include"), "-include", os.path.join(_DIR, "cuda_host_shim.h")]
+    objs = []
+    for src in (os.path.join(_CSRC, "capi_fr.cu"), os.path.join(_CSRC, "capi_h2c.cu"), os.path.join(_DIR, "emul_cabi_ctx.cpp")):
+        obj = os.path.join(_DIR, os.path.basename(src) + ".emul.o")
+        subprocess.check_call(common + ["-x", "c++", "-c", src, "-o", obj])
+        objs.append(obj)
+    subprocess.check_call(["g++", "-shared", "-pthread", "-o", so] + objs)
     open(stamp, "w").write(dg)
     return so

@@ -51,3 +51,18 @@ static inline int __ffs(uint32_t x) { return __builtin_ffs((int)x); }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 using std::min;
 using std::max;
+
+// a kernel "launch": every (block, thread) in turn on the calling host thread.  Only valid for kernels without
+// intra-block cooperation (no __syncthreads / shared memory / shuffles).
+template <class K, class... A>
+static inline void emul_kernel_launch(K k, unsigned grid, unsigned block, A... a) {
+  blockDim = emul_dim3{block, 1, 1};
+  gridDim = emul_dim3{grid, 1, 1};
+  for (unsigned b = 0; b < grid; b++) {
+    blockIdx = emul_dim3{b, 0, 0};
+    for (unsigned t = 0; t < block; t++) {
+      threadIdx = emul_dim3{t, 0, 0};
+      k(a...);
+    }
+  }
+}
