@@ -36,6 +36,8 @@ SIGNATURES = {
     "b200_g1_hash_to_curve": [_vp, _vp, _vp, _sz, _vp, _sz, _i, _vp],
     "b200_g2_hash_to_curve": [_vp, _vp, _vp, _sz, _vp, _sz, _i, _vp],
     "b200_h2c_stage": [_vp, _i, _i, _vp, _sz, _vp],
+    "b200_fr_from_okm": [_vp, _vp, _sz, _vp],
+    "b200_fr_hash_to_field": [_vp, _vp, _vp, _sz, _vp, _sz, _i, _vp],
     "b200_miller_loop_batch": [_vp, _vp, _vp, _vp, _vp, _sz, _vp],
     "b200_final_exponentiation_batch": [_vp, _vp, _sz, _vp],
     "b200_pairing_batch": [_vp, _vp, _vp, _vp, _vp, _sz, _vp],

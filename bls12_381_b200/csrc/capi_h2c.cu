@@ -117,6 +117,42 @@ int b200_g2_hash_to_curve(b200_ctx *ctx, const uint8_t *msgs, const uint64_t *of
   if ((n && (!offsets || !out)) || (dst_len && !dst)) return B200_EINVAL;
   return n ? hash_host(ctx, 2, msgs, offsets, n, dst, dst_len, encode, out) : B200_OK;
 }
+int b200_fr_from_okm(b200_ctx *ctx, const uint8_t *okm, size_t n, b200_fr *out) {
+  CHECK_CTX(ctx);
+  if (n && (!okm || !out)) return B200_EINVAL;
+  if (n == 0) return B200_OK;
+  int rc = stage_reserve(ctx, 48 * n + 32 * n + 4 * 256);
+  if (rc != B200_OK) return rc;
+  uint8_t *din = (uint8_t *)stage_take(ctx, 48 * n);
+  char *dout = (char *)stage_take(ctx, 32 * n);
+  B200_CUDA(ctx, cudaMemcpyAsync(din, okm, 48 * n, cudaMemcpyHostToDevice, ctx->stream));
+  B200_LAUNCH(ctx, k_h2c_fr_from_okm, (unsigned)((n + 127) / 128), 128, 0, (const uint8_t *)din, n, dout);
+  B200_CUDA(ctx, cudaMemcpyAsync(out, dout, 32 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+int b200_fr_hash_to_field(b200_ctx *ctx, const uint8_t *msgs, const uint64_t *offsets, size_t n, const uint8_t *dst, size_t dst_len,
+                          int count, b200_fr *out) {
+  CHECK_CTX(ctx);
+  if (count < 1 || count > 170 || (n && (!offsets || !out)) || (dst_len && !dst)) return B200_EINVAL;  // 48 * count <= 255 * 32
+  if (n == 0) return B200_OK;
+  const size_t len = (size_t)48 * count, ob = 32 * (size_t)count * n;
+  uint8_t *d_msgs, *d_dp, *d_extra;
+  uint64_t *d_off;
+  int dp_len;
+  std::vector<uint64_t> rebased;
+  int rc = stage_inputs(ctx, msgs, offsets, n, dst, dst_len, len * n + 256 + ob, &d_msgs, &d_off, &d_dp, &dp_len, &d_extra, rebased);
+  if (rc != B200_OK) return rc;
+  uint8_t *d_okm = d_extra;
+  char *d_out = (char *)d_extra + ((len * n + 255) & ~(size_t)255);
+  B200_LAUNCH(ctx, k_h2c_expand, (unsigned)((n + 127) / 128), 128, 0, (const uint8_t *)d_msgs, (const uint64_t *)d_off, n,
+              (const uint8_t *)d_dp, dp_len, (uint32_t)len, d_okm);
+  const size_t m = n * (size_t)count;
+  B200_LAUNCH(ctx, k_h2c_fr_from_okm, (unsigned)((m + 127) / 128), 128, 0, (const uint8_t *)d_okm, m, d_out);
+  B200_CUDA(ctx, cudaMemcpyAsync(out, d_out, ob, cudaMemcpyDeviceToHost, ctx->stream));
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
 int b200_h2c_stage(b200_ctx *ctx, int group, int kind, const void *in, size_t n, void *out) {
   CHECK_CTX(ctx);
   if ((group != 1 && group != 2) || kind < 0 || kind > 3 || (n && (!in || !out))) return B200_EINVAL;

@@ -54,6 +54,11 @@ B200_DEV fr fr_r2() {
   fr r = {{0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu, 0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u}};
   return r;
 }
+// R^3 = 2^768 mod q (src/scalar.rs:175-180)
+B200_DEV fr fr_r3() {
+  fr r = {{0x439b73afu, 0xc62c1807u, 0x8cf06990u, 0x1b3e0d18u, 0xc7b5f418u, 0x73d13c71u, 0xc8db33e9u, 0x6e2a5bb9u}};
+  return r;
+}
 // 2^-1 (src/scalar.rs:183-188)
 B200_DEV fr fr_two_inv() {
   fr r = {{0xffffffffu, 0x00000000u, 0x0001a401u, 0xac425bfdu, 0xf65e27fau, 0xccc627f7u, 0xd66282b7u, 0x0c1258acu}};
@@ -257,6 +262,28 @@ B200_DEV fr fr_from_mont(const fr &a) {
 }
 // canonical integer (< q) -> Montgomery (src/scalar.rs:278: tmp *= R2)
 B200_DEV fr fr_to_mont(const fr &a) { return fr_mul(a, fr_r2()); }
+
+// x mod q for any 256-bit x (2^256 < 3q: at most two subtractions)
+B200_DEV fr fr_reduce_256(const fr &x) {
+  fr r = x;
+#pragma unroll 1
+  for (int it = 0; it < 2; it++) {
+    uint32_t t[8], borrow;
+    ptx_sub_cc(t[0], r.v[0], fr_modw(0));
+#pragma unroll
+    for (int k = 1; k < 8; k++) ptx_subc_cc(t[k], r.v[k], fr_modw(k));
+    ptx_subc(borrow, 0u, 0u);
+#pragma unroll
+    for (int k = 0; k < 8; k++) r.v[k] = borrow ? r.v[k] : t[k];
+  }
+  return r;
+}
+// Scalar::from_bytes_wide / from_u512 (src/scalar.rs:300-331): lo + hi * 2^256 as a field element, Montgomery form:
+// lo * R2 + hi * R3.  The reference feeds the raw 256-bit halves to its (wide-product) multiplication; the interleaved
+// multiplication here wants operands < q, so the halves are reduced first — the field element is the same.
+B200_DEV fr fr_from_wide(const fr &lo, const fr &hi) {
+  return fr_add(fr_mul(fr_reduce_256(lo), fr_r2()), fr_mul(fr_reduce_256(hi), fr_r3()));
+}
 
 // ---- global memory <-> registers: 8 consecutive little-endian 32-bit words (== Scalar([u64; 4])), 32 B = one sector
 B200_DEV fr fr_load(const void *p) {

@@ -15,6 +15,7 @@
 #pragma once
 #include "constants.cuh"
 #include "curve.cuh"
+#include "fr.cuh"
 #include "h2c_constants.cuh"
 
 namespace b200 {
@@ -410,6 +411,28 @@ __global__ void __launch_bounds__(128) k_h2c_stage(int kind, const char *in, siz
     else r = kind == 1 ? h2c_g2_iso_map(p) : h2c_g2_clear_cofactor(p);
   }
   proj_store<F>(out + 3 * FB * i, r);
+}
+
+// ------------------------------------------------------------------ hash to field for Scalar
+// src/hash_to_curve/map_scalar.rs:17-22: 48 big-endian uniform bytes, zero-extended to 512 bits, from_bytes_wide
+B200_DEV fr h2c_fr_from_okm(const uint8_t *okm) {
+  fr lo, hi = fr_zero();
+#pragma unroll
+  for (int w = 0; w < 8; w++) {  // little-endian word w of the 384-bit integer = bytes okm[44 - 4w .. 48 - 4w)
+    const uint8_t *q = okm + 44 - 4 * w;
+    lo.v[w] = (uint32_t)q[0] << 24 | (uint32_t)q[1] << 16 | (uint32_t)q[2] << 8 | q[3];
+  }
+#pragma unroll
+  for (int w = 0; w < 4; w++) {
+    const uint8_t *q = okm + 12 - 4 * w;
+    hi.v[w] = (uint32_t)q[0] << 24 | (uint32_t)q[1] << 16 | (uint32_t)q[2] << 8 | q[3];
+  }
+  return fr_from_wide(lo, hi);
+}
+static __global__ void __launch_bounds__(128) k_h2c_fr_from_okm(const uint8_t *okm, size_t n, char *out) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fr_store(out + 32 * i, h2c_fr_from_okm(okm + 48 * i));
 }
 
 // The launch sequence of one batch (shared by capi_h2c.cu and the CPU test harness; `launch` as in fr_ntt.cuh).

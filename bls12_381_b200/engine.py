@@ -246,6 +246,22 @@ class Engine:
                                                                   int(encode), _hp(out)), "hash_to_curve")
         return out
 
+    def fr_from_okm(self, okm):
+        """Scalar::from_okm on (n, 48) uniform bytes -> (n, 4) Montgomery limbs (src/hash_to_curve/map_scalar.rs:17)"""
+        okm = _np(okm, np.uint8, 48)
+        out = np.empty((okm.shape[0], 4), np.uint64)
+        self._ck(self.lib.b200_fr_from_okm(self.h, _hp(okm), okm.shape[0], _hp(out)), "fr_from_okm")
+        return out
+
+    def fr_hash_to_field(self, msgs, dst, count=1):
+        """Scalar::hash_to_field::<ExpandMsgXmd<Sha256>>: `count` scalars per message -> (n * count, 4)"""
+        cat, off = self._pack(msgs)
+        d = np.frombuffer(bytes(dst) or b"\0", np.uint8).copy()
+        out = np.empty((len(msgs) * count, 4), np.uint64)
+        self._ck(self.lib.b200_fr_hash_to_field(self.h, _hp(cat), _hp(off), len(msgs), _hp(d), len(dst), count, _hp(out)),
+                 "fr_hash_to_field")
+        return out
+
     H2C_KIND = dict(sswu=0, iso_map=1, map_to_curve=2, clear_cofactor=3)
 
     def h2c_stage(self, k, kind, a):

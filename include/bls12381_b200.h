@@ -219,6 +219,11 @@ int b200_expand_message_xmd_sha256(b200_ctx *ctx, const uint8_t *msgs, const uin
 int b200_g1_hash_to_curve(b200_ctx *ctx, const uint8_t *msgs, const uint64_t *offsets, size_t n, const uint8_t *dst, size_t dst_len, int encode, b200_g1_projective *out);
 int b200_g2_hash_to_curve(b200_ctx *ctx, const uint8_t *msgs, const uint64_t *offsets, size_t n, const uint8_t *dst, size_t dst_len, int encode, b200_g2_projective *out);
 int b200_h2c_stage(b200_ctx *ctx, int group, int kind, const void *in, size_t n, void *out);
+/* hash to field for Scalar (src/hash_to_curve/map_scalar.rs:10-23, src/hash_to_curve/mod.rs:41-66): b200_fr_from_okm maps
+ * n x 48 uniform bytes to n scalars (Scalar::from_okm); b200_fr_hash_to_field writes `count` scalars per message,
+ * out[i * count + c], from expand_message_xmd(msg_i, dst, 48 * count).  1 <= count <= 170. */
+int b200_fr_from_okm(b200_ctx *ctx, const uint8_t *okm, size_t n, b200_fr *out);
+int b200_fr_hash_to_field(b200_ctx *ctx, const uint8_t *msgs, const uint64_t *offsets, size_t n, const uint8_t *dst, size_t dst_len, int count, b200_fr *out);
 
 /* ---- measurement helper: dependent-free IMAD.WIDE.U32 stream on all SMs; returns achieved
  * 32x32+64 multiply-adds per second (the integer roofline denominator) ------------ */

@@ -297,4 +297,18 @@ static inline bool g2_hash(const uint8_t *msg, size_t msg_len, const uint8_t *ds
   return true;
 }
 
+// ------------------------------------------------------------------ hash to field for Scalar
+// src/hash_to_curve/map_scalar.rs:10-23: 48 uniform bytes, big-endian, zero-extended to 64 and reduced like
+// Scalar::from_bytes_wide (src/scalar.rs:300-331)
+static inline Scalar fr_from_okm(const uint8_t okm[48]) {
+  uint8_t bs[64] = {0};
+  std::memcpy(bs + 16, okm, 48);
+  for (int i = 0; i < 32; i++) {
+    uint8_t t = bs[i];
+    bs[i] = bs[63 - i];
+    bs[63 - i] = t;
+  }
+  return fr_from_bytes_wide(bs);
+}
+
 }  // namespace bls_oracle

@@ -374,6 +374,27 @@ void orc_sgn0(int level, const uint64_t *a, uint8_t *out, size_t n) {
   }
 }
 
+// Scalar::from_okm (src/hash_to_curve/map_scalar.rs:17) on n x 48 bytes, and Scalar::hash_to_field: `count` scalars per
+// message from expand_message_xmd(msg, dst, 48 * count)  (src/hash_to_curve/mod.rs:41-66)
+void orc_fr_from_okm(const uint8_t *okm, uint64_t *out, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    Scalar r = fr_from_okm(okm + 48 * i);
+    std::memcpy(out + 4 * i, &r, 32);
+  }
+}
+int orc_fr_hash_to_field(const uint8_t *msgs, const uint64_t *off, size_t n, const uint8_t *dst, size_t dst_len, int count,
+                         uint64_t *out) {
+  std::vector<uint8_t> okm((size_t)48 * count);
+  for (size_t i = 0; i < n; i++) {
+    if (!expand_message_xmd_sha256(msgs + off[i], (size_t)(off[i + 1] - off[i]), dst, dst_len, okm.size(), okm.data())) return -1;
+    for (int c = 0; c < count; c++) {
+      Scalar r = fr_from_okm(okm.data() + 48 * c);
+      std::memcpy(out + 4 * (i * count + c), &r, 32);
+    }
+  }
+  return 0;
+}
+
 // ---------------------------------------------------------------- G1
 void orc_g1_generator(uint64_t *proj) {
   G1Projective g = g1p_generator();

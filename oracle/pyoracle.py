@@ -245,6 +245,22 @@ def sgn0(level, a):
     return out
 
 
+def fr_from_okm(okm):
+    okm = _u8(okm, 48)
+    out = np.empty((okm.shape[0], 4), np.uint64)
+    lib().orc_fr_from_okm(_p(okm), _p(out), C.c_size_t(okm.shape[0]))
+    return out
+
+
+def fr_hash_to_field(msgs, dst, count=1):
+    cat, off = pack_messages(msgs)
+    dst = _u8(np.frombuffer(bytes(dst), np.uint8))
+    out = np.empty((len(msgs) * count, 4), np.uint64)
+    rc = lib().orc_fr_hash_to_field(_p(cat), _p(off), C.c_size_t(len(msgs)), _p(dst), C.c_size_t(dst.size), count, _p(out))
+    assert rc == 0
+    return out
+
+
 class _Group:
     """G1 (k=1) or G2 (k=2) entry points; coordinates are k*6 limbs wide."""
 

@@ -118,3 +118,7 @@ def test_h2c_batches_stages_and_offsets(eng, orc):
     assert np.array_equal(eng.h2c_stage(1, "map_to_curve", u), orc.h2c_stage("g1_map_to_curve", u))
     u2 = util.rand_fp(rng, 2, 2)
     assert np.array_equal(eng.h2c_stage(2, "sswu", u2), orc.h2c_stage("g2_sswu", u2))
+
+
+def test_hash_to_scalar(eng, orc):
+    H2C.test_hash_to_scalar(eng, orc)

@@ -10,7 +10,7 @@ import pytest
 
 from tests.test_oracle_fr import Q, to_mont, raw, L
 
-pytestmark = [pytest.mark.gpu,
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900),
               pytest.mark.xfail(strict=False, reason="first hardware run pending (round-1 GPU budget exhausted); "
                                                      "validated on the CPU harness")]
 

@@ -163,3 +163,26 @@ def test_batch_layout_and_edge_messages(orc):
     a = orc.hash_to_curve(2, [b"msg"], long_dst)
     b = orc.hash_to_curve(2, [b"msg"], hashlib.sha256(b"H2C-OVERSIZE-DST-" + long_dst).digest())
     assert np.array_equal(a, b)
+
+
+def test_hash_to_scalar(orc):          # src/hash_to_curve/map_scalar.rs:25-45
+    Q = pyref.Q
+    for c in VEC["map_scalar.rs::test_hash_to_scalar"]:
+        got = orc.fr_from_okm(np.frombuffer(bytes.fromhex(c["okm"]), np.uint8))
+        assert int.from_bytes(orc.scalar_to_bytes(got)[0].tobytes(), "little") == int(c["expected"], 16)
+    assert not orc.fr_from_okm(np.zeros(48, np.uint8)).any()            # the all-zero case of the same test
+    rng = np.random.default_rng(8400)
+    okm = np.frombuffer(rng.bytes(48 * 50), np.uint8).reshape(50, 48).copy()
+    okm[0] = 0xff
+    got = orc.scalar_to_bytes(orc.fr_from_okm(okm))
+    for i in range(50):
+        assert int.from_bytes(got[i].tobytes(), "little") == int.from_bytes(okm[i].tobytes(), "big") % Q
+    # hash_to_field: count scalars per message from one expand_message_xmd call (src/hash_to_curve/mod.rs:41-66)
+    msgs, dst = [b"", b"abc", b"x" * 100], b"QUUX-V01-CS02-with-BLS12381SCALAR_XMD:SHA-256_"
+    for count in (1, 2, 3):
+        out = orc.scalar_to_bytes(orc.fr_hash_to_field(msgs, dst, count))
+        for i, m in enumerate(msgs):
+            okm_i = xmd_py(m, dst, 48 * count)
+            for c in range(count):
+                want = int.from_bytes(okm_i[48 * c:48 * c + 48], "big") % Q
+                assert int.from_bytes(out[i * count + c].tobytes(), "little") == want
