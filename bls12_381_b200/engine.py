@@ -175,6 +175,15 @@ class Engine:
             out.append((-k1 if sg[i] & 1 else k1, -k2 if sg[i] & 2 else k2))
         return out
 
+    def gt_mul_batch(self, g, s):
+        """out[i] = &Gt * &Scalar (src/pairings.rs:296-323): (n,72) Fp12 limbs, (n,32) canonical LE scalars"""
+        g, s = _np(g, np.uint64, 72), _np(s, np.uint8, 32)
+        if g.shape[0] != s.shape[0]:
+            raise ValueError("gt_mul_batch: length mismatch")
+        out = np.empty_like(g)
+        self._ck(self.lib.b200_gt_mul_batch(self.h, _hp(g), _hp(s), g.shape[0], _hp(out)), "gt_mul_batch")
+        return out
+
     # ---------------------------------------------------------------- scalar field Fr + NTT (SURVEY §8f row 4)
     FR_OPS = dict(mul=0, add=1, sub=2, square=3, neg=4, invert=5, double=11)
 

@@ -176,6 +176,12 @@ int b200_fp12_product_dev(b200_ctx *ctx, const void *in, size_t n, void *out);
  * bit 1 = k2 < 0. */
 int b200_glv_decompose(b200_ctx *ctx, const b200_scalar *scalars, size_t n, uint8_t *k1k2, uint8_t *signs);
 
+/* ---- Gt * Scalar (`&Gt * &Scalar`, src/pairings.rs:296-323): out[i] = g[i]^scalars[i] in Fp12, double-and-add over the
+ * canonical 32-byte little-endian scalar, limb-identical to the reference for any Fp12 input.  Gt Add / Neg / double /
+ * Sum are b200_tower_op (MUL / CONJUGATE / SQUARE at level 12) and b200_fp12_product_dev. */
+int b200_gt_mul_batch(b200_ctx *ctx, const b200_fp12 *g, const b200_scalar *scalars, size_t n, b200_fp12 *out);
+int b200_gt_mul_batch_dev(b200_ctx *ctx, const void *g, const void *scalars, size_t n, void *out);
+
 /* ---- scalar field Fr: batched arithmetic and the NTT -------------------------------------
  * Elements are b200_fr = Scalar([u64; 4]) (src/scalar.rs:24): little-endian limbs, Montgomery form R = 2^256,
  * canonical (< q).  b200_fr_op: out[i] = a[i] (op) b[i]; op = B200_OP_MUL (src/scalar.rs:554), _ADD (:600), _SUB (:582),

@@ -300,6 +300,29 @@ void orc_fr_ntt(const uint64_t *a, int log_n, int inverse, int coset, uint64_t *
   std::memcpy(out, x.data(), 32 * n);
 }
 
+// ---------------------------------------------------------------- Gt * Scalar (src/pairings.rs:296-323)
+// double-and-add in Fp12, MSB first over the 32-byte LE scalar, leading bit skipped, acc + self computed at every bit and
+// selected — as the reference does
+void orc_gt_mul(const uint64_t *g, const uint8_t *scalars, uint64_t *out, size_t n, int threads) {
+  parallel_for(n, threads, [&](size_t i) {
+    Fp12 x{}, acc = fp12_one();
+    std::memcpy(&x, g + 72 * i, 576);
+    const uint8_t *by = scalars + 32 * i;
+    bool first = true;
+    for (int b = 31; b >= 0; b--)
+      for (int k = 7; k >= 0; k--) {
+        if (first) {
+          first = false;
+          continue;
+        }
+        acc = fp12_square(acc);
+        Fp12 t = fp12_mul(acc, x);
+        if ((by[b] >> k) & 1) acc = t;
+      }
+    std::memcpy(out + 72 * i, &acc, 576);
+  });
+}
+
 // ---------------------------------------------------------------- hash to curve
 int orc_expand_message_xmd_sha256(const uint8_t *msg, size_t msg_len, const uint8_t *dst, size_t dst_len, size_t len_in_bytes,
                                   uint8_t *out) {

@@ -425,6 +425,13 @@ def multi_miller_loop(pxy, pinf, qxy, qinf):
     return out
 
 
+def gt_mul(g, s, threads=1):
+    g, s = _u64(g, 72), _u8(s, 32)
+    out = np.empty_like(g)
+    lib().orc_gt_mul(_p(g), _p(s), _p(out), C.c_size_t(g.shape[0]), threads)
+    return out
+
+
 def g2_prepare(qxy, qinf=0):
     out = np.empty((68, 36), np.uint64)
     n = lib().orc_g2_prepare(_p(_u64(qxy, 24)), int(qinf), _p(out))

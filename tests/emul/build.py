@@ -35,7 +35,7 @@ def build(variant="default"):
 
 
 def build_cabi():
-    """the host side of capi_fr.cu / capi_h2c.cu against the mock CUDA runtime (tests/emul/mock) -> libemul_cabi.so"""
+    """the host side of capi_fr.cu / capi_h2c.cu / capi_gt.cu against the mock CUDA runtime (tests/emul/mock) -> libemul_cabi.so"""
     so = os.path.join(_DIR, "libemul_cabi.so")
     stamp = so + ".stamp"
     dg = _digest("cabi")
@@ -44,7 +44,8 @@ def build_cabi():
     common = ["g++", "-O1", "-std=c++17", "-fPIC", "-pthread", "-Wno-unknown-pragmas", "-I", os.path.join(_DIR, "mock"), "-I", _DIR,
               "-I", _CSRC, "-I", os.path.join(_ROOT, "include"), "-include", os.path.join(_DIR, "cuda_host_shim.h")]
     objs = []
-    for src in (os.path.join(_CSRC, "capi_fr.cu"), os.path.join(_CSRC, "capi_h2c.cu"), os.path.join(_DIR, "emul_cabi_ctx.cpp")):
+    for src in (os.path.join(_CSRC, "capi_fr.cu"), os.path.join(_CSRC, "capi_h2c.cu"), os.path.join(_CSRC, "capi_gt.cu"),
+                os.path.join(_DIR, "emul_cabi_ctx.cpp")):
         obj = os.path.join(_DIR, os.path.basename(src) + ".emul.o")
         subprocess.check_call(common + ["-x", "c++", "-c", src, "-o", obj])
         objs.append(obj)

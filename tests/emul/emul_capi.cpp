@@ -8,6 +8,7 @@
 #include "fp_inv.cuh"
 #include "glv.cuh"
 #include "pairing.cuh"
+#include "gt.cuh"
 #ifdef EMUL_WITH_FR
 #include "fr_ntt.cuh"
 #include "h2c.cuh"
@@ -186,6 +187,14 @@ void emul_miller_loop_prepared(const char *pxy, int pinf, const char *coeffs, in
   fp12 f;
   miller_loop_prepared(&f, affine_load<fp>(pxy, &flag, 0), coeffs, qinf != 0);
   fp12_store(out, &f);
+}
+void emul_gt_mul(const char *g, const uint32_t *s, size_t n, char *out, int threads) {
+  par_for(n, threads, [=](size_t i) {
+    fp12 x, acc;
+    fp12_load(&x, g + 576 * i);
+    gt_mul_scalar(&acc, &x, s + 8 * i);
+    fp12_store(out + 576 * i, &acc);
+  });
 }
 // out: k1[4] k2[4] neg1 neg2 (10 words per scalar)
 void emul_glv_decompose(const uint32_t *s, size_t n, uint32_t *out) {

@@ -122,3 +122,12 @@ def test_h2c_batches_stages_and_offsets(eng, orc):
 
 def test_hash_to_scalar(eng, orc):
     H2C.test_hash_to_scalar(eng, orc)
+
+
+def test_gt_mul(eng, orc):
+    from tests.test_gt_mul import _inputs
+    rng, _, g, s = _inputs(orc, 4, 12400)
+    assert np.array_equal(eng.gt_mul_batch(g, s), orc.gt_mul(g, s, threads=4))
+    assert eng.gt_mul_batch(g[:0], s[:0]).shape == (0, 72)
+    with pytest.raises(ValueError):
+        eng.gt_mul_batch(g, s[:2])
