@@ -101,4 +101,52 @@ impl Engine {
         }
         Ok((0..n).map(|i| st[i] & 1 == 1 && chk[i] == 3).collect())
     }
+
+    /// In-place FFT over `Scalar::ROOT_OF_UNITY` (src/scalar.rs:200) of `a.len() = 2^k` scalars — forward, inverse (with
+    /// the 1/n scaling) and the coset variants bellman's `EvaluationDomain` uses.  Marshalled through
+    /// `Scalar::to_bytes` / `from_bytes` and converted to/from Montgomery limbs on the GPU.
+    pub fn fft(&self, a: &mut [Scalar], inverse: bool, coset: bool) -> Result<(), Error> {
+        let n = a.len();
+        assert!(n.is_power_of_two());
+        let k = n.trailing_zeros() as c_int;
+        let enc: Vec<sys::b200_scalar> = a.iter().map(|s| sys::b200_scalar { b: s.to_bytes() }).collect();
+        let mut limbs = vec![sys::b200_fr { l: [0; 4] }; n];
+        let mut ok = vec![0u8; n];
+        let mut out = vec![sys::b200_scalar { b: [0; 32] }; n];
+        unsafe {
+            check(sys::b200_fr_from_bytes(self.0, enc.as_ptr(), n, limbs.as_mut_ptr(), ok.as_mut_ptr()))?;
+            check(sys::b200_fr_ntt(self.0, limbs.as_ptr(), k, inverse as c_int, coset as c_int, limbs.as_mut_ptr()))?;
+            check(sys::b200_fr_to_bytes(self.0, limbs.as_ptr(), n, out.as_mut_ptr()))?;
+        }
+        for (x, y) in a.iter_mut().zip(&out) {
+            *x = Scalar::from_bytes(&y.b).unwrap();
+        }
+        Ok(())
+    }
+
+    /// `<G1Projective as HashToCurve<ExpandMsgXmd<Sha256>>>::hash_to_curve(msg, dst)` for every message
+    /// (src/hash_to_curve/mod.rs:86-92; feature "experimental" of the reference), one GPU thread per message.
+    pub fn g1_hash_to_curve(&self, msgs: &[&[u8]], dst: &[u8]) -> Result<Vec<G1Projective>, Error> {
+        let n = msgs.len();
+        let mut off = Vec::with_capacity(n + 1);
+        let mut cat = Vec::new();
+        off.push(0u64);
+        for m in msgs {
+            cat.extend_from_slice(m);
+            off.push(cat.len() as u64);
+        }
+        let z = sys::b200_fp { l: [0; 6] };
+        let mut pr = vec![sys::b200_g1_projective { x: z, y: z, z }; n];
+        let mut xy = vec![sys::b200_g1_affine { x: z, y: z }; n];
+        let mut inf = vec![0u8; n];
+        let mut enc = vec![0u8; 96 * n];
+        unsafe {
+            check(sys::b200_g1_hash_to_curve(self.0, cat.as_ptr(), off.as_ptr(), n, dst.as_ptr(), dst.len(), 0, pr.as_mut_ptr()))?;
+            check(sys::b200_g1_batch_normalize(self.0, pr.as_ptr(), n, xy.as_mut_ptr(), inf.as_mut_ptr()))?;
+            check(sys::b200_g1_serialize(self.0, xy.as_ptr(), inf.as_ptr(), n, 0, enc.as_mut_ptr()))?;
+        }
+        Ok(enc.chunks_exact(96)
+            .map(|c| G1Projective::from(G1Affine::from_uncompressed_unchecked(c.try_into().unwrap()).unwrap()))
+            .collect())
+    }
 }

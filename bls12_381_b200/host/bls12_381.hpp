@@ -200,6 +200,13 @@ inline std::vector<G2Projective> hash_to_curve_g2(const Engine &e, const std::ve
 
 struct Gt {
   b200_fp12 v;  // canonical Fp12 (src/pairings.rs:211)
+  // out[i] = &g[i] * &scalars[i]   (src/pairings.rs:296-323)
+  static std::vector<Gt> mul_batch(const Engine &e, const std::vector<Gt> &g, const std::vector<Scalar> &scalars) {
+    if (g.size() != scalars.size()) throw Error(B200_EINVAL, "Gt::mul_batch: length mismatch");
+    std::vector<Gt> out(g.size());
+    e.check(b200_gt_mul_batch(e.raw(), &g.data()->v, &scalars.data()->bytes, g.size(), &out.data()->v), "gt_mul_batch");
+    return out;
+  }
 };
 
 struct MillerLoopResult {
