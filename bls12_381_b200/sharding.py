@@ -6,6 +6,9 @@ exchange their 144-byte (G1) / 288-byte (G2) partials with ONE all_gather, and e
 locally with complete projective additions (`b200_g{1,2}_sum_dev`).  NCCL has no elliptic-curve reduction
 operator, so "allreduce of partial sums" = all_gather + local add.
 Pairing batches / scalar-mul batches shard by index with no collective (`index_range`).
+The pairing PRODUCT (multi_miller_loop over n terms, SURVEY §8e "mode ii") shards by term index: every rank multiplies
+the Miller-loop values of its terms into one Fp12, the ranks exchange those 576-byte partials with one all_gather,
+multiply them, and one final exponentiation follows (`ShardedPairingProduct`).
 """
 import torch
 
@@ -52,4 +55,49 @@ class ShardedMSM:
             self.eng.msm_dev(self.k, xy[lo:hi], None if inf is None else inf[lo:hi], scalars[lo:hi], hi - lo, out)
         self._gather(parts, out)
         self.eng.sum_dev(self.k, parts, self.world, out)
+        return out
+
+
+# Fp12::one() as 72 little-endian u64 limbs viewed as int64 (c0.c0.c0 = R = 2^384 mod p, src/fp.rs:83-90)
+_FP12_ONE = [0x760900000002fffd, 0xebf4000bc40c0002, 0x5f48985753c758ba, 0x77ce585370525745, 0x5c071a97a256ec6d,
+             0x15f65ec3fa80e493] + [0] * 66
+
+
+def _to_i64(v):
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
+class ShardedPairingProduct:
+    """multi_miller_loop(&[(p_i, q_i)]) (src/pairings.rs:554-603) over n terms held by every rank, sharded by term index.
+    `engine` needs miller_loop_batch_dev(p, pinf, q, qinf, n, out), fp12_product_dev(f, n, out) and
+    final_exponentiation_batch_dev(f, n, out).  The product of per-term Miller values equals the reference's shared-
+    squaring loop value (f <- f^2 * prod l_i), and identity terms contribute one(), so the MillerLoopResult — and the
+    Gt after final_exponentiation — are limb-identical to the single-GPU / reference result."""
+
+    def __init__(self, engine, dist=None, stream=None):
+        self.eng, self.dist, self.stream = engine, dist, stream
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.world = dist.get_world_size() if dist is not None else 1
+
+    def multi_miller_loop(self, p, pinf, q, qinf, n, out, parts, scratch, final_exp=False):
+        """out (1, 72) <- product over all n terms on every rank.  p (n,12), q (n,24) affine limbs, pinf/qinf (n,) uint8
+        or None; parts = (world, 72) and scratch = (ceil(n / world), 72) int64 work tensors on the engine's device."""
+        lo, hi = index_range(n, self.rank, self.world)
+        m = hi - lo
+        local = parts[self.rank:self.rank + 1] if self.world == 1 else out
+        if m == 0:
+            local.copy_(torch.tensor([_to_i64(v) for v in _FP12_ONE], dtype=torch.int64).reshape(1, 72))
+        else:
+            sl = lambda t: None if t is None else t[lo:hi]
+            self.eng.miller_loop_batch_dev(p[lo:hi], sl(pinf), q[lo:hi], sl(qinf), m, scratch)
+            self.eng.fp12_product_dev(scratch, m, local)
+        if self.world > 1:
+            if self.stream is not None:
+                with torch.cuda.stream(self.stream):
+                    self.dist.all_gather_into_tensor(parts, local)
+            else:
+                self.dist.all_gather_into_tensor(parts, local)
+        self.eng.fp12_product_dev(parts, self.world, out)
+        if final_exp:
+            self.eng.final_exponentiation_batch_dev(out, 1, out)
         return out

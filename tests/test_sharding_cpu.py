@@ -43,6 +43,69 @@ class OracleEngine:
         out.copy_(torch.from_numpy(acc.view(np.int64)))
 
 
+    # ---- pairing product stand-ins
+    def miller_loop_batch_dev(self, p, pinf, q, qinf, n, out):
+        r = self.o.miller_loop(p.numpy().view(np.uint64)[:n], None if pinf is None else pinf.numpy()[:n],
+                               q.numpy().view(np.uint64)[:n], None if qinf is None else qinf.numpy()[:n], threads=2)
+        out[:n].copy_(torch.from_numpy(r.view(np.int64)))
+
+    def fp12_product_dev(self, f, n, out):
+        a = f.numpy().view(np.uint64)
+        acc = a[0:1].copy()
+        for i in range(1, n):
+            acc = self.o.tower(12, "mul", acc, a[i:i + 1])
+        out.copy_(torch.from_numpy(acc.view(np.int64)))
+
+    def final_exponentiation_batch_dev(self, f, n, out):
+        r = self.o.final_exponentiation(f.numpy().view(np.uint64)[:n])
+        out[:n].copy_(torch.from_numpy(r.view(np.int64)))
+
+
+def _pair_worker(rank, world, port, n, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from bls12_381_b200.sharding import ShardedPairingProduct
+    from oracle import pyoracle as o
+    rng = np.random.default_rng(77)                       # replicated inputs
+    t = rng.integers(0, 256, (2 * n, 32), dtype=np.uint8)
+    t[:, 31] &= 0x3f
+    pxy, pinf = o.G1.batch_normalize(o.G1.mul(np.repeat(o.G1.generator(), n, 0), t[:n]))
+    qxy, qinf = o.G2.batch_normalize(o.G2.mul(np.repeat(o.G2.generator(), n, 0), t[n:]))
+    if n > 2:
+        pinf[1] = 1                                       # identity terms are skipped (src/pairings.rs:566-569)
+        qinf[n - 1] = 1
+    T = lambda a: torch.from_numpy(a.view(np.int64) if a.dtype == np.uint64 else a)
+    out = torch.zeros((1, 72), dtype=torch.int64)
+    parts = torch.zeros((world, 72), dtype=torch.int64)
+    scratch = torch.zeros(((n + world - 1) // world, 72), dtype=torch.int64)
+    sp = ShardedPairingProduct(OracleEngine(), dist=dist)
+    sp.multi_miller_loop(T(pxy), T(pinf), T(qxy), T(qinf), n, out, parts, scratch)
+    want = o.multi_miller_loop(pxy, pinf, qxy, qinf)       # the reference's shared-squaring loop, restated
+    ok = bool(np.array_equal(out.numpy().view(np.uint64), want))
+    sp.multi_miller_loop(T(pxy), T(pinf), T(qxy), T(qinf), n, out, parts, scratch, final_exp=True)
+    ok &= bool(np.array_equal(out.numpy().view(np.uint64), o.final_exponentiation(want)))
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 5), (3, 2)])
+def test_sharded_pairing_product_gloo(orc, world, n):
+    """SURVEY §8(e) "pairing product": terms sharded by index, one all_gather of 576-byte partials, local product, one
+    final exponentiation — equal to the single-process multi_miller_loop; (3, 2) leaves one rank without terms"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29950 + (os.getpid() % 40) + world
+    procs = [ctx.Process(target=_pair_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(r, True) for r in range(world)]
+
+
 def _worker(rank, world, port, mode, k, q):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
