@@ -3,8 +3,10 @@
 // compare it with the oracle without a GPU.  Built twice: default (lazy-reduction Fp2, the G2/MSM translation units)
 // and -DB200_FP2_KCALL (the pairing translation units).
 #include "cuda_host_shim.h"
+#include "fiber_warp.h"
 
 #include "curve.cuh"
+#include "curve_warp.cuh"
 #include "fp_inv.cuh"
 #include "glv.cuh"
 #include "pairing.cuh"
@@ -187,6 +189,61 @@ void emul_miller_loop_prepared(const char *pxy, int pinf, const char *coeffs, in
   fp12 f;
   miller_loop_prepared(&f, affine_load<fp>(pxy, &flag, 0), coeffs, qinf != 0);
   fp12_store(out, &f);
+}
+}  // extern "C"
+namespace {
+// the body of capi_basic.cu::k_mul_batch_warp: ONE WARP per item, lane-parallel group operations of curve_warp.cuh
+// (shuffles) — run on the fiber scheduler of fiber_warp.h
+template <class F>
+void k_emul_mul_batch_warp(const char *p, const uint32_t *s, char *out, size_t n) {
+  size_t item = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (item >= n) return;
+  constexpr size_t PB = 3 * field_traits<F>::bytes;
+  uint32_t by[8];
+  memcpy(by, s + 8 * item, 32);
+  proj<F> base = proj_load<F>(p + PB * item), acc = proj_identity<F>();
+  for (int bit = 254; bit >= 0; bit--) {
+    acc = warp_double(acc, lane);
+    if ((by[bit >> 5] >> (bit & 31)) & 1) acc = warp_add(acc, base, lane);
+  }
+  if (lane == 0) proj_store<F>(out + PB * item, acc);
+}
+}  // namespace
+extern "C" {
+// 128-thread blocks = 4 items per block, like the GPU launch
+void emul_g1_mul_warp(const char *p, const uint32_t *s, char *out, size_t n) {
+  emul_cooperative_launch(k_emul_mul_batch_warp<fp>, (unsigned)((n * 32 + 127) / 128), 128u, p, s, out, n);
+}
+void emul_g2_mul_warp(const char *p, const uint32_t *s, char *out, size_t n) {
+  emul_cooperative_launch(k_emul_mul_batch_warp<fp2>, (unsigned)((n * 32 + 127) / 128), 128u, p, s, out, n);
+}
+// self-test of the fiber scheduler: block reduction through shared memory + __syncthreads, warp sums through
+// __shfl_down_sync, a ballot and an early-exiting warp
+int emul_fiber_selftest(unsigned block, const int *in, int n, int *block_sum, int *warp_sums, unsigned *ballots) {
+  static int sh[1024];
+  auto kernel = [](const int *in, int n, int *block_sum, int *warp_sums, unsigned *ballots) {
+    unsigned t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (w == 1 && blockDim.x > 64) return;          // a whole warp leaves early: barriers must not wait for it
+    int v = (int)t < n ? in[t] : 0;
+    sh[t] = v;
+    __syncthreads();
+    for (unsigned st = 1; st < blockDim.x; st <<= 1) {    // naive tree, every level separated by a barrier
+      int add = (t % (2 * st) == 0 && t + st < blockDim.x) ? sh[t + st] : 0;
+      __syncthreads();
+      sh[t] += add;
+      __syncthreads();
+    }
+    if (t == 0) *block_sum = sh[0];
+    int x = v;
+    for (int d = 16; d > 0; d >>= 1) x += __shfl_down_sync(0xffffffffu, x, d);
+    if (lane == 0) warp_sums[w] = x;
+    unsigned b = __ballot_sync(0xffffffffu, v & 1);
+    if (lane == 0) ballots[w] = b;
+  };
+  for (unsigned i = 0; i < block; i++) sh[i] = 0;
+  emul_cooperative_launch(kernel, 1u, block, in, n, block_sum, warp_sums, ballots);
+  return 0;
 }
 void emul_gt_mul(const char *g, const uint32_t *s, size_t n, char *out, int threads) {
   par_for(n, threads, [=](size_t i) {
