@@ -6,7 +6,13 @@ where /root/reference exists; the outputs are committed so the GPU box never nee
                       compressed/uncompressed; src/tests/mod.rs:3-76), stored as uint8 arrays.
  * kat.json         : every 64-bit hex literal of the known-answer tests listed in SURVEY.md §8(c),
                       in source order, grouped 6-per-Fp (4-per-Scalar), keyed "file::function".
-                      tests/test_oracle_golden.py documents how each list is interpreted.
+                      tests/test_oracle_golden.py documents how each list is interpreted.  Also the scalar-field
+                      constants of src/scalar.rs:76-222 ("scalar.rs::const_*"), the byte vectors of its
+                      test_to_bytes / test_from_bytes, and src/hash_to_curve/map_g1.rs::test_simple_swu_expected.
+ * h2c_vectors.json : the RFC 9380 (draft-16) vectors of the reference's integration tests — tests/expand_msg.rs
+                      (expand_message_xmd, SHA-256, short and long DST), tests/hash_to_curve_g1.rs and _g2.rs
+                      (hash_to_curve / encode_to_curve, uncompressed encodings) — and
+                      src/hash_to_curve/map_scalar.rs::test_hash_to_scalar, all as hex strings.
 """
 import json, re, sys, os
 import numpy as np
