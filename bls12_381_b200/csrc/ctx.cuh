@@ -53,6 +53,9 @@ struct b200_ctx {
   // scalar-field NTT tables of capi_fr.cu (twiddles + coset powers for the last log_n used); freed by ctx_destroy
   void *fr_state = nullptr;
   void (*fr_state_free)(void *) = nullptr;
+  // Miller loop / final exponentiation kernels: 4 = pairing_v4.cu (validated, default), 5 = pairing_v5.cu (experimental
+  // dual-stream Fp2 multiply; CPU-validated, to be measured in round 2)
+  int tune_pairing_variant = 4;
 };
 
 namespace b200 {

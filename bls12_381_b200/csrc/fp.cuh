@@ -184,6 +184,72 @@ B200_DEV fp fp_sqr(const fp &a) { return fp_mul(a, a); }
 static __device__ __noinline__ fp fp_mul_c(fp a, fp b) { return fp_mul(a, b); }
 
 // ---------------------------------------------------------------------------------------------------
+// TWO independent products with their rows alternated: (a*b, c*d).  Each product is the dependent carry-chain stream
+// of fp_mul; one warp alone cannot keep the multiplier busy with it (ncu, pairing kernels: the `wait` stall — fixed-
+// latency dependency — is 3.3-3.6 cycles per issue at 2 warps per scheduler).  Emitting the chains of two products
+// next to each other (a whole chain at a time: PTX has a single CC.CF, so chains cannot be interleaved instruction by
+// instruction in the source — ptxas renames the carries into predicate registers and overlaps adjacent independent
+// chains) gives the scheduler two independent streams per warp.  Same values as two fp_mul calls.
+// EXPERIMENTAL (round 2 candidate): used only by the B200_FP2_KDUAL variant of fp2.cuh / pairing_v5.cu; CPU-validated,
+// not yet measured.
+struct fp_pair {
+  fp r0, r1;
+};
+B200_DEV fp fp_mul_tail(const uint32_t *ev, const uint32_t *od) {
+  fp r;
+  ptx_add_cc(r.v[0], ev[0], od[1]);
+#pragma unroll
+  for (int k = 1; k < 11; k++) ptx_addc_cc(r.v[k], ev[k], od[k + 1]);
+  ptx_addc(r.v[11], ev[11], 0u);
+  uint32_t t[12], borrow;
+  ptx_sub_cc(t[0], r.v[0], fp_modw(0));
+#pragma unroll
+  for (int k = 1; k < 12; k++) ptx_subc_cc(t[k], r.v[k], fp_modw(k));
+  ptx_subc(borrow, 0u, 0u);
+#pragma unroll
+  for (int k = 0; k < 12; k++) r.v[k] = borrow ? r.v[k] : t[k];
+  return r;
+}
+// one interleaved-Montgomery row of fp_mul on (A, B) = (the accumulator that is word-aligned after the shift, the other)
+B200_DEV void fp_mul_row_acc(uint32_t *A, uint32_t *B, const fp &x, uint32_t y) {
+  ptx_add_cc(A[0], A[0], B[1]);
+  fp_madc_rshift_row(B, x.v + 1, y);
+  fp_cmad_row(A, x.v, y);
+  ptx_addc(B[11], B[11], 0u);
+}
+B200_DEV fp_pair fp_mul_dual(const fp &a, const fp &b, const fp &c, const fp &d) {
+  uint32_t ev0[12], od0[12], ev1[12], od1[12];
+#pragma unroll
+  for (int j = 0; j < 12; j += 2) {
+    ptx_mul_lo(ev0[j], a.v[j], b.v[0]);
+    ptx_mul_hi(ev0[j + 1], a.v[j], b.v[0]);
+    ptx_mul_lo(od0[j], a.v[j + 1], b.v[0]);
+    ptx_mul_hi(od0[j + 1], a.v[j + 1], b.v[0]);
+    ptx_mul_lo(ev1[j], c.v[j], d.v[0]);
+    ptx_mul_hi(ev1[j + 1], c.v[j], d.v[0]);
+    ptx_mul_lo(od1[j], c.v[j + 1], d.v[0]);
+    ptx_mul_hi(od1[j + 1], c.v[j + 1], d.v[0]);
+  }
+  fp_redc_step(ev0, od0);
+  fp_redc_step(ev1, od1);
+#pragma unroll
+  for (int i = 1; i < 12; i += 2) {
+    fp_mul_row_acc(od0, ev0, a, b.v[i]);
+    fp_mul_row_acc(od1, ev1, c, d.v[i]);
+    fp_redc_step(od0, ev0);
+    fp_redc_step(od1, ev1);
+    if (i + 1 < 12) {
+      fp_mul_row_acc(ev0, od0, a, b.v[i + 1]);
+      fp_mul_row_acc(ev1, od1, c, d.v[i + 1]);
+      fp_redc_step(ev0, od0);
+      fp_redc_step(ev1, od1);
+    }
+  }
+  return fp_pair{fp_mul_tail(ev0, od0), fp_mul_tail(ev1, od1)};
+}
+static __device__ __noinline__ fp_pair fp_mul2_c(fp a, fp b, fp c, fp d) { return fp_mul_dual(a, b, c, d); }
+
+// ---------------------------------------------------------------------------------------------------
 // Lazy reduction support (used by the Fp2 multiplication): an unreduced 768-bit product, its Montgomery
 // reduction, and plain (non-modular) 384/768-bit add/sub.  Karatsuba Fp2 mul = 3 wide products (3 x 144
 // IMAD) + 2 reductions (2 x 156) = 744 IMAD instead of 3 x 300 = 900.  8p < 2^384 leaves room for the

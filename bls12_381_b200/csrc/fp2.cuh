@@ -70,6 +70,7 @@ B200_DEV void fp2_store(void *p, const fp2 &a) {
 //   B200_FP2_KCALL     Karatsuba over three calls of fp_mul_c: shortest dependent chains; best for the
 //                      latency-bound pairing kernels (2 warps per SMSP), where the lazy variant is 9 % slower.
 //   B200_FP2_KINLINE   Karatsuba with the three/two Fp products inlined side by side (more ILP for ptxas).
+//   B200_FP2_KDUAL     EXPERIMENTAL: two of the products in one row-alternating routine (fp_mul_dual) — not measured yet.
 #if defined(B200_FP2_KCALL)
 B200_NOINL fp2 fp2_mul_c(fp2 a, fp2 b) {
   fp t0 = fp_mul_c(a.c0, b.c0);
@@ -80,6 +81,19 @@ B200_NOINL fp2 fp2_mul_c(fp2 a, fp2 b) {
 B200_NOINL fp2 fp2_sqr_c(fp2 a) {
   fp s = fp_add(a.c0, a.c1), d = fp_sub(a.c0, a.c1), t = fp_dbl(a.c0);
   return fp2{fp_mul_c(s, d), fp_mul_c(t, a.c1)};
+}
+#elif defined(B200_FP2_KDUAL)
+// EXPERIMENTAL (pairing_v5.cu): Karatsuba with the two independent products a0*b0, a1*b1 computed by ONE call whose
+// rows alternate (fp_mul_dual) — two dependent streams per warp instead of one; the squaring's two products likewise.
+B200_NOINL fp2 fp2_mul_c(fp2 a, fp2 b) {
+  fp_pair t = fp_mul2_c(a.c0, b.c0, a.c1, b.c1);
+  fp s = fp_mul_c(fp_add(a.c0, a.c1), fp_add(b.c0, b.c1));
+  return fp2{fp_sub(t.r0, t.r1), fp_sub(fp_sub(s, t.r0), t.r1)};
+}
+B200_NOINL fp2 fp2_sqr_c(fp2 a) {
+  fp s = fp_add(a.c0, a.c1), d = fp_sub(a.c0, a.c1), t = fp_dbl(a.c0);
+  fp_pair p = fp_mul2_c(s, d, t, a.c1);
+  return fp2{p.r0, p.r1};
 }
 #elif defined(B200_FP2_KINLINE)
 B200_NOINL fp2 fp2_mul_c(fp2 a, fp2 b) { return fp2_mul(a, b); }

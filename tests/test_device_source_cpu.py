@@ -37,7 +37,7 @@ class Emul:
         f(*[_p(a) if isinstance(a, np.ndarray) or a is None else a for a in arrs], *extra)
 
 
-@pytest.fixture(scope="module", params=["default", "kcall"])
+@pytest.fixture(scope="module", params=["default", "kcall", "kdual"])
 def em(request):
     return Emul(request.param)
 
@@ -51,7 +51,7 @@ def test_fp_limb_algorithms(em, orc):
     a = np.concatenate([util.rand_fp(rng, 200), util.edge_fp(), util.edge_fp()[::-1]])
     b = np.concatenate([util.rand_fp(rng, 200), util.edge_fp(), util.edge_fp()])
     want_mul, want_sq = orc.tower(1, "mul", a, b), orc.tower(1, "square", a)
-    for code in (0, 100, 101):      # interleaved product, its called copy, wide product + REDC
+    for code in (0, 100, 101, 104, 105):      # interleaved product, its called copy, wide product + REDC, dual-stream
         assert np.array_equal(em.tower(1, code, a, b), want_mul)
     for code in (3, 102):           # dedicated squaring (78 + 156 IMAD), mul(a, a)
         assert np.array_equal(em.tower(1, code, a), want_sq)
