@@ -389,7 +389,7 @@ int b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int value) {
   } else if (!strcmp(key, "g1_prefetch")) {
     ctx->tune_g1_prefetch = value != 0;
   } else if (!strcmp(key, "pairing_variant")) {
-    if (value != 4 && value != 5) return B200_EINVAL;
+    if (value < 4 || value > 6) return B200_EINVAL;
     ctx->tune_pairing_variant = value;
   } else if (!strcmp(key, "pairing_chunks")) {
     if (value < 1 || value > 64) return B200_EINVAL;

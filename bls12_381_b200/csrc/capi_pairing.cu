@@ -15,6 +15,7 @@ using namespace b200;
                                     size_t, void *);
 DECL_VARIANT(v4)
 DECL_VARIANT(v5)
+DECL_VARIANT(v6)
 
 namespace {
 
@@ -24,10 +25,12 @@ namespace {
 int miller_on(b200_ctx *ctx, cudaStream_t st, const void *p, const void *pi, const void *q, const void *qi, size_t n,
               void *out) {
   if (ctx->tune_pairing_variant == 5) return b200_pair_miller_v5(ctx, st, p, pi, q, qi, n, out);  // experimental (pairing_v5.cu)
+  if (ctx->tune_pairing_variant == 6) return b200_pair_miller_v6(ctx, st, p, pi, q, qi, n, out);  // experimental (pairing_v6.cu)
   return b200_pair_miller_v4(ctx, st, p, pi, q, qi, n, out);
 }
 int final_exp_on(b200_ctx *ctx, cudaStream_t st, const void *in, size_t n, void *out) {
   if (ctx->tune_pairing_variant == 5) return b200_pair_final_exp_v5(ctx, st, in, n, out);
+  if (ctx->tune_pairing_variant == 6) return b200_pair_final_exp_v6(ctx, st, in, n, out);
   return b200_pair_final_exp_v4(ctx, st, in, n, out);
 }
 int miller_dev(b200_ctx *ctx, const void *p, const void *pi, const void *q, const void *qi, size_t n, void *out) {

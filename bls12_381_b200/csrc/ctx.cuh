@@ -53,8 +53,8 @@ struct b200_ctx {
   // scalar-field NTT tables of capi_fr.cu (twiddles + coset powers for the last log_n used); freed by ctx_destroy
   void *fr_state = nullptr;
   void (*fr_state_free)(void *) = nullptr;
-  // Miller loop / final exponentiation kernels: 4 = pairing_v4.cu (validated, default), 5 = pairing_v5.cu (experimental
-  // dual-stream Fp2 multiply; CPU-validated, to be measured in round 2)
+  // Miller loop / final exponentiation kernels: 4 = pairing_v4.cu (validated, default), 5 = pairing_v5.cu / 6 =
+  // pairing_v6.cu (experimental dual- / triple-stream Fp2 multiply; CPU-validated, to be measured in round 2)
   int tune_pairing_variant = 4;
 };
 

@@ -248,6 +248,50 @@ B200_DEV fp_pair fp_mul_dual(const fp &a, const fp &b, const fp &c, const fp &d)
   return fp_pair{fp_mul_tail(ev0, od0), fp_mul_tail(ev1, od1)};
 }
 static __device__ __noinline__ fp_pair fp_mul2_c(fp a, fp b, fp c, fp d) { return fp_mul_dual(a, b, c, d); }
+// THREE products with alternated rows (a*b, c*d, e*f): the whole Karatsuba Fp2 multiplication as one routine
+// (B200_FP2_KTRIPLE, pairing_v6.cu).  EXPERIMENTAL, same status as fp_mul_dual.
+struct fp_triple {
+  fp r0, r1, r2;
+};
+B200_DEV fp_triple fp_mul_triple(const fp &a, const fp &b, const fp &c, const fp &d, const fp &e, const fp &f) {
+  uint32_t ev0[12], od0[12], ev1[12], od1[12], ev2[12], od2[12];
+#pragma unroll
+  for (int j = 0; j < 12; j += 2) {
+    ptx_mul_lo(ev0[j], a.v[j], b.v[0]);
+    ptx_mul_hi(ev0[j + 1], a.v[j], b.v[0]);
+    ptx_mul_lo(od0[j], a.v[j + 1], b.v[0]);
+    ptx_mul_hi(od0[j + 1], a.v[j + 1], b.v[0]);
+    ptx_mul_lo(ev1[j], c.v[j], d.v[0]);
+    ptx_mul_hi(ev1[j + 1], c.v[j], d.v[0]);
+    ptx_mul_lo(od1[j], c.v[j + 1], d.v[0]);
+    ptx_mul_hi(od1[j + 1], c.v[j + 1], d.v[0]);
+    ptx_mul_lo(ev2[j], e.v[j], f.v[0]);
+    ptx_mul_hi(ev2[j + 1], e.v[j], f.v[0]);
+    ptx_mul_lo(od2[j], e.v[j + 1], f.v[0]);
+    ptx_mul_hi(od2[j + 1], e.v[j + 1], f.v[0]);
+  }
+  fp_redc_step(ev0, od0);
+  fp_redc_step(ev1, od1);
+  fp_redc_step(ev2, od2);
+#pragma unroll
+  for (int i = 1; i < 12; i += 2) {
+    fp_mul_row_acc(od0, ev0, a, b.v[i]);
+    fp_mul_row_acc(od1, ev1, c, d.v[i]);
+    fp_mul_row_acc(od2, ev2, e, f.v[i]);
+    fp_redc_step(od0, ev0);
+    fp_redc_step(od1, ev1);
+    fp_redc_step(od2, ev2);
+    if (i + 1 < 12) {
+      fp_mul_row_acc(ev0, od0, a, b.v[i + 1]);
+      fp_mul_row_acc(ev1, od1, c, d.v[i + 1]);
+      fp_mul_row_acc(ev2, od2, e, f.v[i + 1]);
+      fp_redc_step(ev0, od0);
+      fp_redc_step(ev1, od1);
+      fp_redc_step(ev2, od2);
+    }
+  }
+  return fp_triple{fp_mul_tail(ev0, od0), fp_mul_tail(ev1, od1), fp_mul_tail(ev2, od2)};
+}
 
 // ---------------------------------------------------------------------------------------------------
 // Lazy reduction support (used by the Fp2 multiplication): an unreduced 768-bit product, its Montgomery

@@ -71,6 +71,7 @@ B200_DEV void fp2_store(void *p, const fp2 &a) {
 //                      latency-bound pairing kernels (2 warps per SMSP), where the lazy variant is 9 % slower.
 //   B200_FP2_KINLINE   Karatsuba with the three/two Fp products inlined side by side (more ILP for ptxas).
 //   B200_FP2_KDUAL     EXPERIMENTAL: two of the products in one row-alternating routine (fp_mul_dual) — not measured yet.
+//   B200_FP2_KTRIPLE   EXPERIMENTAL: all three in one routine (fp_mul_triple) — not measured yet.
 #if defined(B200_FP2_KCALL)
 B200_NOINL fp2 fp2_mul_c(fp2 a, fp2 b) {
   fp t0 = fp_mul_c(a.c0, b.c0);
@@ -93,6 +94,18 @@ B200_NOINL fp2 fp2_mul_c(fp2 a, fp2 b) {
 B200_NOINL fp2 fp2_sqr_c(fp2 a) {
   fp s = fp_add(a.c0, a.c1), d = fp_sub(a.c0, a.c1), t = fp_dbl(a.c0);
   fp_pair p = fp_mul2_c(s, d, t, a.c1);
+  return fp2{p.r0, p.r1};
+}
+#elif defined(B200_FP2_KTRIPLE)
+// EXPERIMENTAL (pairing_v6.cu): all three Karatsuba products in one row-alternating routine (fp_mul_triple, inlined
+// into the called Fp2 multiply: operands arrive in registers anyway); the squaring uses the dual routine.
+B200_NOINL fp2 fp2_mul_c(fp2 a, fp2 b) {
+  fp_triple t = fp_mul_triple(a.c0, b.c0, a.c1, b.c1, fp_add(a.c0, a.c1), fp_add(b.c0, b.c1));
+  return fp2{fp_sub(t.r0, t.r1), fp_sub(fp_sub(t.r2, t.r0), t.r1)};
+}
+B200_NOINL fp2 fp2_sqr_c(fp2 a) {
+  fp s = fp_add(a.c0, a.c1), d = fp_sub(a.c0, a.c1), t = fp_dbl(a.c0);
+  fp_pair p = fp_mul_dual(s, d, t, a.c1);
   return fp2{p.r0, p.r1};
 }
 #elif defined(B200_FP2_KINLINE)

@@ -1,6 +1,6 @@
-"""GPU parity test (-m gpu) of the EXPERIMENTAL pairing kernels (pairing_v5.cu: dual-stream Fp2 multiply, tuning key
-pairing_variant = 5) against the oracle and against the default kernels.  CPU-validated (tests/test_device_source_cpu.py,
-variant "kdual"); first hardware run pending -> non-strict xfail.  The default (pairing_variant = 4) is untouched."""
+"""GPU parity test (-m gpu) of the EXPERIMENTAL pairing kernels (pairing_v5.cu / pairing_v6.cu: dual- / triple-stream Fp2 multiply, tuning
+key pairing_variant = 5 / 6) against the oracle and against the default kernels.  CPU-validated (tests/test_device_source_cpu.py,
+variants "kdual" / "ktriple"); first hardware run pending -> non-strict xfail.  The default (pairing_variant = 4) is untouched."""
 import numpy as np
 import pytest
 
@@ -10,7 +10,8 @@ pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900),
               pytest.mark.xfail(strict=False, reason="first hardware run pending (round-1 GPU budget exhausted)")]
 
 
-def test_pairing_variant_5_parity(orc):
+@pytest.mark.parametrize("variant", [5, 6])
+def test_pairing_variant_parity(orc, variant):
     import bls12_381_b200
     eng = bls12_381_b200.Engine()
     try:
@@ -22,7 +23,7 @@ def test_pairing_variant_5_parity(orc):
         qinf[9] = 1
         base = eng.pairing_batch(pxy, pinf, qxy, qinf)
         ml4 = eng.miller_loop_batch(pxy, pinf, qxy, qinf)
-        eng.set_tuning("pairing_variant", 5)
+        eng.set_tuning("pairing_variant", variant)
         got = eng.pairing_batch(pxy, pinf, qxy, qinf)
         ml5 = eng.miller_loop_batch(pxy, pinf, qxy, qinf)
         fe5 = eng.final_exponentiation_batch(ml5)
@@ -30,6 +31,6 @@ def test_pairing_variant_5_parity(orc):
         assert np.array_equal(got, base) and np.array_equal(ml5, ml4) and np.array_equal(fe5, base)
         assert np.array_equal(got[:64], orc.pairing(pxy[:64], pinf[:64], qxy[:64], qinf[:64], threads=8))
         with pytest.raises(bls12_381_b200.B200Error):
-            eng.set_tuning("pairing_variant", 6)
+            eng.set_tuning("pairing_variant", 7)
     finally:
         eng.close()

@@ -13,6 +13,7 @@ python bench.py --steps 10 --warmup 3 > gpurun_out/r02_bench_g1msm.json 2> gpuru
 # the experimental dual-stream pairing kernels against the default ones (same workload, same process conditions)
 python bench.py --workload pairing --steps 5 --warmup 3 > gpurun_out/r02_bench_pairing_v4.json 2> gpurun_out/r02_bench_pairing.err
 python bench.py --workload pairing --steps 5 --warmup 3 --tune pairing_variant=5 > gpurun_out/r02_bench_pairing_v5.json 2>> gpurun_out/r02_bench_pairing.err
+python bench.py --workload pairing --steps 5 --warmup 3 --tune pairing_variant=6 > gpurun_out/r02_bench_pairing_v6.json 2>> gpurun_out/r02_bench_pairing.err
 # launch list + one full capture of the NTT pass kernel (skip the table-building launches of the first call)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r02_ncu_launches_fr_ntt.csv \
     python tools/bench_fr_ntt.py --log-n 22 --steps 2 --warmup 1 --cpu-log-n 12 > /dev/null 2>&1
