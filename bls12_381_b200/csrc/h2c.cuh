@@ -220,7 +220,7 @@ static __device__ __noinline__ void h2c_add(proj<fp2> *r, const proj<fp2> *a, co
 static __device__ __noinline__ void h2c_dbl(proj<fp2> *r, const proj<fp2> *a) { *r = proj_double(*a); }
 // [x]P, x = -0xd201000000010000 (src/g1.rs:777-795, src/g2.rs:915-932)
 template <class F>
-B200_DEV proj<F> h2c_mul_by_x(const proj<F> &s) {
+static __device__ __noinline__ proj<F> h2c_mul_by_x(const proj<F> &s) {
   proj<F> xself = proj_identity<F>(), acc = s;
   unsigned long long x = 0xd201000000010000ull >> 1;
 #pragma unroll 1
@@ -234,7 +234,7 @@ B200_DEV proj<F> h2c_mul_by_x(const proj<F> &s) {
 
 // ------------------------------------------------------------------ G1
 // src/hash_to_curve/map_g1.rs:550-586
-B200_DEV proj<fp> h2c_g1_sswu(const fp &u) {
+static __device__ __noinline__ proj<fp> h2c_g1_sswu(const fp &u) {
   const fp A = h2c_const(H2C_G1_SSWU_ELLP_A, 0), B = h2c_const(H2C_G1_SSWU_ELLP_B, 0), XI = h2c_const(H2C_G1_SSWU_XI, 0);
   fp usq = fp_sqr_c(u), xi_usq = fp_mul_c(XI, usq), xisq_u4 = fp_sqr_c(xi_usq);
   fp nd_common = fp_add(xisq_u4, xi_usq);
@@ -261,7 +261,7 @@ B200_DEV fp h2c_g1_iso_poly(const uint32_t (*coeff)[12], const fp &x, const fp *
   return v;
 }
 // src/hash_to_curve/map_g1.rs:589-631
-B200_DEV proj<fp> h2c_g1_iso_map(const proj<fp> &u) {
+static __device__ __noinline__ proj<fp> h2c_g1_iso_map(const proj<fp> &u) {
   fp zpows[15];
   zpows[0] = u.z;
 #pragma unroll 1
@@ -277,7 +277,7 @@ B200_DEV proj<fp> h2c_g1_iso_map(const proj<fp> &u) {
 }
 B200_DEV proj<fp> h2c_g1_map_to_curve(const fp &u) { return h2c_g1_iso_map(h2c_g1_sswu(u)); }
 // src/g1.rs:800-802: self - [x]self
-B200_DEV proj<fp> h2c_g1_clear_cofactor(const proj<fp> &p) {
+static __device__ __noinline__ proj<fp> h2c_g1_clear_cofactor(const proj<fp> &p) {
   proj<fp> m = proj_neg(h2c_mul_by_x(p)), r;
   h2c_add(&r, &p, &m);
   return r;
@@ -285,7 +285,7 @@ B200_DEV proj<fp> h2c_g1_clear_cofactor(const proj<fp> &p) {
 
 // ------------------------------------------------------------------ G2
 // src/hash_to_curve/map_g2.rs:391-454
-B200_DEV proj<fp2> h2c_g2_sswu(const fp2 &u) {
+static __device__ __noinline__ proj<fp2> h2c_g2_sswu(const fp2 &u) {
   const fp2 A = h2c_const2(H2C_G2_SSWU_ELLP_A, 0), B = h2c_const2(H2C_G2_SSWU_ELLP_B, 0), XI = h2c_const2(H2C_G2_SSWU_XI, 0);
   fp2 usq = S2(u), xi_usq = M2(XI, usq), xisq_u4 = S2(xi_usq);
   fp2 nd_common = fp2_add(xisq_u4, xi_usq);
@@ -328,7 +328,7 @@ B200_DEV fp2 h2c_g2_iso_poly(const uint32_t (*coeff)[12], const fp2 &x, const fp
   return v;
 }
 // src/hash_to_curve/map_g2.rs:457-493
-B200_DEV proj<fp2> h2c_g2_iso_map(const proj<fp2> &u) {
+static __device__ __noinline__ proj<fp2> h2c_g2_iso_map(const proj<fp2> &u) {
   fp2 zpows[3];
   zpows[0] = u.z;
   zpows[1] = S2(u.z);
@@ -353,7 +353,7 @@ B200_DEV proj<fp2> h2c_psi2(const proj<fp2> &s) {
   return proj<fp2>{M2(s.x, cx), fp2_neg(s.y), s.z};
 }
 // src/g2.rs:938-947, the same operator order
-B200_DEV proj<fp2> h2c_g2_clear_cofactor(const proj<fp2> &p) {
+static __device__ __noinline__ proj<fp2> h2c_g2_clear_cofactor(const proj<fp2> &p) {
   proj<fp2> t1 = h2c_mul_by_x(p), t2 = h2c_psi(p), d, s, r;
   h2c_dbl(&d, &p);
   d = h2c_psi2(d);
