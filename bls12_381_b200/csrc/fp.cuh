@@ -486,6 +486,105 @@ B200_DEV fpw fp_sqr_wide(const fp &a) {
   }
   return t;
 }
+// Row-alternated versions of the lazy-reduction building blocks (EXPERIMENTAL, round 2 candidate for the G2 bucket
+// kernel, which sits at 65 % of the multiplier with the plain versions; used only by B200_FP2_LAZY3): three unreduced
+// products with their rows alternated, and two Montgomery reductions with their steps alternated.
+struct fpw3 {
+  fpw w0, w1, w2;
+};
+B200_DEV fpw fpw_join(const uint32_t *E, const uint32_t *O) {
+  fpw t;
+  t.v[0] = E[0];
+  ptx_add_cc(t.v[1], E[1], O[0]);
+#pragma unroll
+  for (int k = 2; k < 23; k++) ptx_addc_cc(t.v[k], E[k], O[k - 1]);
+  ptx_addc(t.v[23], E[23], O[22]);
+  return t;
+}
+template <int I>
+B200_DEV void fp_mul_wide_rows(uint32_t *E, uint32_t *O, const fp &a, const fp &b) {  // rows I and I+1 of fp_mul_wide
+  fp_cmad_row_c<true>(E + I, a.v, b.v[I]);
+  fp_cmad_row_c<true>(O + I, a.v + 1, b.v[I]);
+  fp_cmad_row_c<true>(O + I, a.v, b.v[I + 1]);
+  if (I + 14 < 24)
+    fp_cmad_row_c<true>(E + I + 2, a.v + 1, b.v[I + 1]);
+  else
+    fp_cmad_row_c<false>(E + I + 2, a.v + 1, b.v[I + 1]);
+}
+template <int I>
+B200_DEV void fp_mul_wide_rows3(uint32_t *E0, uint32_t *O0, uint32_t *E1, uint32_t *O1, uint32_t *E2, uint32_t *O2, const fp &a,
+                                const fp &b, const fp &c, const fp &d, const fp &e, const fp &f) {
+  fp_mul_wide_rows<I>(E0, O0, a, b);
+  fp_mul_wide_rows<I>(E1, O1, c, d);
+  fp_mul_wide_rows<I>(E2, O2, e, f);
+}
+B200_DEV fpw3 fp_mul_wide_triple(const fp &a, const fp &b, const fp &c, const fp &d, const fp &e, const fp &f) {
+  uint32_t E0[24], O0[24], E1[24], O1[24], E2[24], O2[24];
+#pragma unroll
+  for (int k = 0; k < 24; k++) E0[k] = O0[k] = E1[k] = O1[k] = E2[k] = O2[k] = 0;
+  fp_mul_wide_rows3<0>(E0, O0, E1, O1, E2, O2, a, b, c, d, e, f);
+  fp_mul_wide_rows3<2>(E0, O0, E1, O1, E2, O2, a, b, c, d, e, f);
+  fp_mul_wide_rows3<4>(E0, O0, E1, O1, E2, O2, a, b, c, d, e, f);
+  fp_mul_wide_rows3<6>(E0, O0, E1, O1, E2, O2, a, b, c, d, e, f);
+  fp_mul_wide_rows3<8>(E0, O0, E1, O1, E2, O2, a, b, c, d, e, f);
+  fp_mul_wide_rows3<10>(E0, O0, E1, O1, E2, O2, a, b, c, d, e, f);
+  return fpw3{fpw_join(E0, O0), fpw_join(E1, O1), fpw_join(E2, O2)};
+}
+// one shift-and-reduce step of fp_redc_wide on (A aligned at word 0 after the shift, B shifted in by two words)
+B200_DEV void fp_redc_wide_step(uint32_t *A, uint32_t *B) {
+  ptx_add_cc(A[0], A[0], B[1]);
+#pragma unroll
+  for (int k = 0; k < 10; k++) ptx_addc_cc(B[k], B[k + 2], 0u);
+  ptx_addc_cc(B[10], 0u, 0u);
+  B[11] = 0;
+  fp_redc_step(A, B);
+}
+B200_DEV fp fp_redc_wide_tail(const uint32_t *ev, const uint32_t *od, const fpw &t) {
+  fp r;
+  ptx_add_cc(r.v[0], ev[0], od[1]);
+#pragma unroll
+  for (int k = 1; k < 11; k++) ptx_addc_cc(r.v[k], ev[k], od[k + 1]);
+  ptx_addc(r.v[11], ev[11], 0u);
+  ptx_add_cc(r.v[0], r.v[0], t.v[12]);
+#pragma unroll
+  for (int k = 1; k < 11; k++) ptx_addc_cc(r.v[k], r.v[k], t.v[12 + k]);
+  ptx_addc(r.v[11], r.v[11], t.v[23]);
+  uint32_t d[12], borrow;
+  ptx_sub_cc(d[0], r.v[0], fp_modw(0));
+#pragma unroll
+  for (int k = 1; k < 12; k++) ptx_subc_cc(d[k], r.v[k], fp_modw(k));
+  ptx_subc(borrow, 0u, 0u);
+#pragma unroll
+  for (int k = 0; k < 12; k++) r.v[k] = borrow ? r.v[k] : d[k];
+  return r;
+}
+B200_DEV fp_pair fp_redc_wide_dual(const fpw &t0, const fpw &t1) {
+  uint32_t ev0[12], od0[12], ev1[12], od1[12];
+#pragma unroll
+  for (int j = 0; j < 12; j += 2) {
+    ev0[j] = t0.v[j];
+    ev0[j + 1] = 0;
+    od0[j] = t0.v[j + 1];
+    od0[j + 1] = 0;
+    ev1[j] = t1.v[j];
+    ev1[j + 1] = 0;
+    od1[j] = t1.v[j + 1];
+    od1[j + 1] = 0;
+  }
+  fp_redc_step(ev0, od0);
+  fp_redc_step(ev1, od1);
+#pragma unroll
+  for (int i = 1; i < 12; i += 2) {
+    fp_redc_wide_step(od0, ev0);
+    fp_redc_wide_step(od1, ev1);
+    if (i + 1 < 12) {
+      fp_redc_wide_step(ev0, od0);
+      fp_redc_wide_step(ev1, od1);
+    }
+  }
+  return fp_pair{fp_redc_wide_tail(ev0, od0, t0), fp_redc_wide_tail(ev1, od1, t1)};
+}
+
 // a^2 * R^-1 mod p, canonical (same value as src/fp.rs:613-660): 78 + 156 = 234 IMAD instead of 305
 B200_DEV fp fp_sqr_fast(const fp &a) { return fp_redc_wide(fp_sqr_wide(a)); }
 static __device__ __noinline__ fp fp_sqr_c(fp a) { return fp_sqr_fast(a); }

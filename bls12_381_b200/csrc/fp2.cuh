@@ -72,6 +72,7 @@ B200_DEV void fp2_store(void *p, const fp2 &a) {
 //   B200_FP2_KINLINE   Karatsuba with the three/two Fp products inlined side by side (more ILP for ptxas).
 //   B200_FP2_KDUAL     EXPERIMENTAL: two of the products in one row-alternating routine (fp_mul_dual) — not measured yet.
 //   B200_FP2_KTRIPLE   EXPERIMENTAL: all three in one routine (fp_mul_triple) — not measured yet.
+//   B200_FP2_LAZY3     EXPERIMENTAL: the lazy variant with row-alternated wide products / reductions — not measured yet.
 #if defined(B200_FP2_KCALL)
 B200_NOINL fp2 fp2_mul_c(fp2 a, fp2 b) {
   fp t0 = fp_mul_c(a.c0, b.c0);
@@ -94,6 +95,19 @@ B200_NOINL fp2 fp2_mul_c(fp2 a, fp2 b) {
 B200_NOINL fp2 fp2_sqr_c(fp2 a) {
   fp s = fp_add(a.c0, a.c1), d = fp_sub(a.c0, a.c1), t = fp_dbl(a.c0);
   fp_pair p = fp_mul2_c(s, d, t, a.c1);
+  return fp2{p.r0, p.r1};
+}
+#elif defined(B200_FP2_LAZY3)
+// EXPERIMENTAL: the default lazy-reduction multiply with its three wide products and its two reductions row-alternated
+// (fp_mul_wide_triple, fp_redc_wide_dual) — candidate for the G2 bucket kernel (65 % of the multiplier in round 1).
+B200_NOINL fp2 fp2_mul_c(fp2 a, fp2 b) {
+  fpw3 w = fp_mul_wide_triple(a.c0, b.c0, a.c1, b.c1, fp_add_nr(a.c0, a.c1), fp_add_nr(b.c0, b.c1));
+  fp_pair r = fp_redc_wide_dual(fpw_sub(w.w2, fpw_add(w.w0, w.w1)), fpw_sub_mod(w.w0, w.w1));
+  return fp2{r.r1, r.r0};
+}
+B200_NOINL fp2 fp2_sqr_c(fp2 a) {
+  fp s = fp_add(a.c0, a.c1), d = fp_sub(a.c0, a.c1), t = fp_dbl(a.c0);
+  fp_pair p = fp_mul_dual(s, d, t, a.c1);
   return fp2{p.r0, p.r1};
 }
 #elif defined(B200_FP2_KTRIPLE)

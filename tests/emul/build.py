@@ -21,7 +21,8 @@ def build(variant="default"):
     """variant: 'default' (lazy-reduction Fp2: capi_basic/capi_msm/capi_serial), 'kcall' (pairing units) or 'kdual'
     (the experimental dual-stream Fp2 of pairing_v5.cu)"""
     so = os.path.join(_DIR, "libemul_%s.so" % variant)
-    flags = {"kcall": ["-DB200_FP2_KCALL"], "kdual": ["-DB200_FP2_KDUAL"], "ktriple": ["-DB200_FP2_KTRIPLE"]}.get(variant, [])
+    flags = {"kcall": ["-DB200_FP2_KCALL"], "kdual": ["-DB200_FP2_KDUAL"], "ktriple": ["-DB200_FP2_KTRIPLE"],
+             "lazy3": ["-DB200_FP2_LAZY3"]}.get(variant, [])
     if os.path.exists(os.path.join(_CSRC, "fr.cuh")):
         flags.append("-DEMUL_WITH_FR")
     stamp = so + ".stamp"
