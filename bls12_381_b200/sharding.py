@@ -70,7 +70,8 @@ def _to_i64(v):
 class ShardedPairingProduct:
     """multi_miller_loop(&[(p_i, q_i)]) (src/pairings.rs:554-603) over n terms held by every rank, sharded by term index.
     `engine` needs miller_loop_batch_dev(p, pinf, q, qinf, n, out), fp12_product_dev(f, n, out) and
-    final_exponentiation_batch_dev(f, n, out).  The product of per-term Miller values equals the reference's shared-
+    final_exponentiation_batch_dev(f, n, out); `stream` = the engine's CUDA stream (torch.cuda.ExternalStream), so the
+    collective is ordered with the engine's kernels, as in ShardedMSM.  The product of per-term Miller values equals the reference's shared-
     squaring loop value (f <- f^2 * prod l_i), and identity terms contribute one(), so the MillerLoopResult — and the
     Gt after final_exponentiation — are limb-identical to the single-GPU / reference result."""
 
@@ -85,8 +86,13 @@ class ShardedPairingProduct:
         lo, hi = index_range(n, self.rank, self.world)
         m = hi - lo
         local = parts[self.rank:self.rank + 1] if self.world == 1 else out
-        if m == 0:
-            local.copy_(torch.tensor([_to_i64(v) for v in _FP12_ONE], dtype=torch.int64).reshape(1, 72))
+        if m == 0:                              # more ranks than terms: this rank contributes Fp12::one()
+            one = torch.tensor([_to_i64(v) for v in _FP12_ONE], dtype=torch.int64).reshape(1, 72)
+            if self.stream is not None:         # same stream as the collective below
+                with torch.cuda.stream(self.stream):
+                    local.copy_(one)
+            else:
+                local.copy_(one)
         else:
             sl = lambda t: None if t is None else t[lo:hi]
             self.eng.miller_loop_batch_dev(p[lo:hi], sl(pinf), q[lo:hi], sl(qinf), m, scratch)

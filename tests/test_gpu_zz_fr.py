@@ -137,6 +137,7 @@ def test_ntt_dev_in_place(eng, orc):
     a = rand_fr(rng, 1 << log_n)
     t = torch.from_numpy(a.view(np.int64)).cuda()
     out = torch.empty_like(t)
+    torch.cuda.synchronize()              # the engine works on its own non-blocking stream
     eng.fr_ntt_dev(t, log_n, out)
     eng.fr_ntt_dev(t, log_n, t)           # in == out
     torch.cuda.synchronize()

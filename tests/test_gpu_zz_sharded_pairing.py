@@ -27,12 +27,14 @@ def test_pairing_product_one_rank(orc):
         parts = torch.zeros((1, 72), dtype=torch.int64, device="cuda")
         scratch = torch.zeros((n, 72), dtype=torch.int64, device="cuda")
         sp = ShardedPairingProduct(eng)
-        sp.multi_miller_loop(dev(pxy), dev(pinf), dev(qxy), dev(qinf), n, out, parts, scratch)
+        dp, dpi, dq, dqi = dev(pxy), dev(pinf), dev(qxy), dev(qinf)
+        torch.cuda.synchronize()              # the engine works on its own non-blocking stream
+        sp.multi_miller_loop(dp, dpi, dq, dqi, n, out, parts, scratch)
         torch.cuda.synchronize()
         want = orc.multi_miller_loop(pxy, pinf, qxy, qinf)
         assert np.array_equal(out.cpu().numpy().view(np.uint64), want)
         assert np.array_equal(eng.multi_miller_loop(pxy, pinf, qxy, qinf), want)      # the single-call entry point agrees
-        sp.multi_miller_loop(dev(pxy), dev(pinf), dev(qxy), dev(qinf), n, out, parts, scratch, final_exp=True)
+        sp.multi_miller_loop(dp, dpi, dq, dqi, n, out, parts, scratch, final_exp=True)
         torch.cuda.synchronize()
         assert np.array_equal(out.cpu().numpy().view(np.uint64), orc.final_exponentiation(want))
     finally:

@@ -41,6 +41,7 @@ def main():
     dev = torch.from_numpy(host.view(np.int64)).cuda()
     out = torch.empty_like(dev)
     back = torch.empty_like(dev)
+    torch.cuda.synchronize()                       # the engine works on its own non-blocking stream
     eng.fr_ntt_dev(dev, a.log_n, out)
     eng.fr_ntt_dev(out, a.log_n, back, inverse=True)
     torch.cuda.synchronize()
