@@ -14,6 +14,8 @@ python bench.py --steps 10 --warmup 3 > gpurun_out/r02_bench_g1msm.json 2> gpuru
 python bench.py --workload pairing --steps 5 --warmup 3 > gpurun_out/r02_bench_pairing_v4.json 2> gpurun_out/r02_bench_pairing.err
 python bench.py --workload pairing --steps 5 --warmup 3 --tune pairing_variant=5 > gpurun_out/r02_bench_pairing_v5.json 2>> gpurun_out/r02_bench_pairing.err
 python bench.py --workload pairing --steps 5 --warmup 3 --tune pairing_variant=6 > gpurun_out/r02_bench_pairing_v6.json 2>> gpurun_out/r02_bench_pairing.err
+# default G2 MSM vs the experimental second build of the MSM unit (row-alternated lazy Fp2 multiply)
+python tools/bench_g2_msm_variant.py --log-n 20 --steps 5 --warmup 2 > gpurun_out/r02_g2_msm_variant.json 2> gpurun_out/r02_g2_msm_variant.err
 # launch list + one full capture of the NTT pass kernel (skip the table-building launches of the first call)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r02_ncu_launches_fr_ntt.csv \
     python tools/bench_fr_ntt.py --log-n 22 --steps 2 --warmup 1 --cpu-log-n 12 > /dev/null 2>&1
