@@ -1,6 +1,6 @@
 #!/bin/bash
-# First GPU call of the next round (run under gpurun from the repo root, ~10 GPU-minutes):
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_first_call_round2.sh'
+# First GPU call of the next round (run under gpurun from the repo root, ~20-25 GPU-minutes):
+#   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash tools/gpu_first_call_round2.sh'
 # 1. the validated gate, 2. the two rows written after round 1's GPU budget ran out (scalar field / NTT, hash to curve:
 # expect XPASS — then delete the xfail markers in tests/test_gpu_zz_*.py), 3. their first measurements and ncu captures.
 set -u
