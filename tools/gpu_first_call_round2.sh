@@ -21,5 +21,10 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --c
     python tools/bench_fr_ntt.py --log-n 22 --steps 2 --warmup 1 --cpu-log-n 12 > /dev/null 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_fr_ntt_pass -s 8 -c 1 -o gpurun_out/r02_ncu_fr_ntt_pass \
     python tools/bench_fr_ntt.py --log-n 22 --steps 1 --warmup 1 --cpu-log-n 12 > /dev/null 2>&1
+# per-kernel times of the pairing variants (ncu serialises and runs cold: compare shares, not absolutes)
+for v in 4 5 6; do
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r02_ncu_launches_pairing_v$v.csv \
+      python bench.py --workload pairing --steps 1 --warmup 1 --tune pairing_variant=$v > /dev/null 2>&1
+done
 cat gpurun_out/r02_first_pytest.txt | tail -15
 cat gpurun_out/r02_fr_ntt_2p24.json
