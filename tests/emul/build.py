@@ -54,3 +54,25 @@ def build_cabi():
     subprocess.check_call(["g++", "-shared", "-pthread", "-o", so] + objs)
     open(stamp, "w").write(dg)
     return so
+
+
+def build_cabi_pairing():
+    """capi_pairing.cu + pairing_v4/v5/v6.cu against the mock runtime, every launch on the fiber scheduler (the product
+    kernel uses __syncthreads and dynamic shared memory) -> libemul_cabi_pairing.so"""
+    so = os.path.join(_DIR, "libemul_cabi_pairing.so")
+    stamp = so + ".stamp"
+    dg = _digest("cabi_pairing")
+    if os.path.exists(so) and os.path.exists(stamp) and open(stamp).read() == dg:
+        return so
+    common = ["g++", "-O1", "-std=c++17", "-fPIC", "-pthread", "-Wno-unknown-pragmas", "-DEMUL_LAUNCH_COOPERATIVE",
+              "-DEMUL_DYNAMIC_SMEM_BYTES=40960", "-Wno-unused-variable", "-I", os.path.join(_DIR, "mock"), "-I", _DIR, "-I", _CSRC, "-I", os.path.join(_ROOT, "include"),
+              "-include", os.path.join(_DIR, "cuda_host_shim.h")]
+    objs = []
+    for src in [os.path.join(_CSRC, f) for f in ("capi_pairing.cu", "pairing_v4.cu", "pairing_v5.cu", "pairing_v6.cu")] + \
+            [os.path.join(_DIR, "emul_cabi_pairing_ctx.cpp")]:
+        obj = os.path.join(_DIR, os.path.basename(src) + ".emulp.o")
+        subprocess.check_call(common + ["-x", "c++", "-c", src, "-o", obj])
+        objs.append(obj)
+    subprocess.check_call(["g++", "-shared", "-pthread", "-o", so] + objs)
+    open(stamp, "w").write(dg)
+    return so

@@ -24,6 +24,7 @@
 #define __forceinline__ inline
 #define __noinline__ __attribute__((noinline))
 #define __launch_bounds__(...)
+#define __shared__   /* only the `extern __shared__ T smem[];` form is supported: the harness defines `smem` */
 #define __restrict__
 
 struct uint4 {
@@ -52,6 +53,21 @@ static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((ui
 using std::min;
 using std::max;
 
+#ifdef EMUL_DYNAMIC_SMEM_BYTES
+// `extern __shared__ char smem[];` inside a kernel of the translation unit's unnamed namespace names a member of that
+// namespace: define it here (this header is force-included first; all unnamed namespaces of a TU are one namespace)
+namespace {
+alignas(16) char smem[EMUL_DYNAMIC_SMEM_BYTES];
+}
+#endif
+#ifdef EMUL_LAUNCH_COOPERATIVE
+// every launch goes through the fiber scheduler of fiber_warp.h (kernels with __syncthreads / shuffles / shared memory)
+#include "fiber_warp.h"
+template <class K, class... A>
+static inline void emul_kernel_launch(K k, unsigned grid, unsigned block, A... a) {
+  emul_cooperative_launch(k, grid, block, a...);
+}
+#else
 // a kernel "launch": every (block, thread) in turn on the calling host thread.  Only valid for kernels without
 // intra-block cooperation (no __syncthreads / shared memory / shuffles).
 template <class K, class... A>
@@ -66,3 +82,4 @@ static inline void emul_kernel_launch(K k, unsigned grid, unsigned block, A... a
     }
   }
 }
+#endif

@@ -39,4 +39,5 @@ static inline cudaError_t cudaEventCreate(cudaEvent_t *e) {
   return cudaSuccess;
 }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
 static inline const char *cudaGetErrorString(cudaError_t) { return "mock CUDA error"; }

@@ -1,0 +1,105 @@
+"""The pairing units of the C ABI (capi_pairing.cu + pairing_v4 / v5 / v6.cu: launch wrappers, variant dispatch by the
+tuning key pairing_variant, chunked two-stream schedule, product kernel with __syncthreads + dynamic shared memory,
+prepared Miller loop) compiled with g++ against the mock CUDA runtime, every launch on the fiber scheduler, and driven
+through the real Engine methods — against the oracle.  CPU only; complements tests/test_gpu_parity.py (v4, validated on
+hardware) and tests/test_gpu_zz_pairing_v5.py (v5 / v6, hardware run pending)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests import util
+from tests.emul import build as emul_build
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from bls12_381_b200 import _lib
+    from bls12_381_b200.engine import Engine
+    lib = C.CDLL(emul_build.build_cabi_pairing())
+    for name, args in _lib.SIGNATURES.items():
+        if hasattr(lib, name):
+            f = getattr(lib, name)
+            f.argtypes = args
+            f.restype = _lib._RESTYPE.get(name, C.c_int)
+
+    class MockEngine(Engine):
+        def __init__(self):
+            self.lib = lib
+            h = C.c_void_p()
+            assert lib.b200_ctx_create(0, C.byref(h)) == 0
+            self.h = h
+
+        def close(self):
+            if self.h:
+                lib.b200_ctx_destroy(self.h)
+                self.h = None
+
+    e = MockEngine()
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def pairs(orc):
+    rng = np.random.default_rng(17100)
+    n = 7
+    _, pxy, pinf = util.rand_points(orc, 1, rng, n)
+    _, qxy, qinf = util.rand_points(orc, 2, rng, n)
+    pinf[2] = 1
+    qinf[5] = 1
+    return pxy, pinf, qxy, qinf
+
+
+@pytest.mark.parametrize("variant", [4, 5, 6])
+def test_variants_through_the_c_abi(eng, orc, pairs, variant):
+    pxy, pinf, qxy, qinf = pairs
+    eng.set_tuning("pairing_variant", variant)
+    try:
+        ml = eng.miller_loop_batch(pxy, pinf, qxy, qinf)
+        want_ml = orc.miller_loop(pxy, pinf, qxy, qinf, threads=7)
+        assert np.array_equal(ml, want_ml)
+        assert np.array_equal(eng.final_exponentiation_batch(ml), orc.final_exponentiation(want_ml, threads=7))
+        assert np.array_equal(eng.pairing_batch(pxy, pinf, qxy, qinf), orc.pairing(pxy, pinf, qxy, qinf, threads=7))
+    finally:
+        eng.set_tuning("pairing_variant", 4)
+
+
+def test_product_and_prepared_paths(eng, orc, pairs):
+    pxy, pinf, qxy, qinf = pairs
+    want = orc.multi_miller_loop(pxy, pinf, qxy, qinf)
+    assert np.array_equal(eng.multi_miller_loop(pxy, pinf, qxy, qinf), want)          # k_fp12_product: barriers + smem
+    co = eng.g2_prepare(qxy, qinf)
+    assert np.array_equal(co[0].reshape(68, 36), orc.g2_prepare(qxy[0:1], int(qinf[0])))
+    assert np.array_equal(eng.multi_miller_loop_prepared(pxy, pinf, co, qinf), want)
+    assert np.array_equal(eng.multi_miller_loop(pxy[:1], pinf[:1], qxy[:1], qinf[:1]),
+                          orc.multi_miller_loop(pxy[:1], pinf[:1], qxy[:1], qinf[:1]))
+
+
+def test_tuning_key_validation(eng):
+    from bls12_381_b200 import B200Error
+    for bad in (3, 7):
+        with pytest.raises(B200Error):
+            eng.set_tuning("pairing_variant", bad)
+    with pytest.raises(B200Error):
+        eng.set_tuning("no_such_key", 1)
+
+
+def test_chunked_schedule(eng, orc):
+    """pairing_dev's chunked two-stream path (taken above sm_count * 256 + 2048 pairs; the mock ctx has sm_count = 1):
+    chunk boundaries, 64-alignment of the chunk size, the ragged last chunk"""
+    rng = np.random.default_rng(17200)
+    n = 2400
+    _, pxy, pinf = util.rand_points(orc, 1, rng, 40)
+    _, qxy, qinf = util.rand_points(orc, 2, rng, 40)
+    idx = rng.integers(0, 40, n)
+    jdx = rng.integers(0, 40, n)
+    P, PI, Qx, QI = pxy[idx], pinf[idx].copy(), qxy[jdx], qinf[jdx].copy()
+    PI[700] = 1
+    QI[2399] = 1
+    eng.set_tuning("pairing_chunks", 3)
+    try:
+        got = eng.pairing_batch(P, PI, Qx, QI)
+    finally:
+        eng.set_tuning("pairing_chunks", 4)
+    assert np.array_equal(got, orc.pairing(P, PI, Qx, QI, threads=8))
