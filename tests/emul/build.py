@@ -12,7 +12,7 @@ def _digest(extra):
     h = hashlib.sha256(extra.encode())
     for d in (_DIR, _CSRC):
         for f in sorted(os.listdir(d)):
-            if f.endswith((".cuh", ".h", ".cpp", ".inc", ".cu")):
+            if f.endswith((".cuh", ".h", ".cpp", ".inc", ".cu", "build.py")):
                 h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()
 
@@ -37,7 +37,7 @@ def build(variant="default"):
 
 
 def build_cabi():
-    """the host side of capi_fr.cu / capi_h2c.cu / capi_gt.cu against the mock CUDA runtime (tests/emul/mock) -> libemul_cabi.so"""
+    """the host side of capi_fr.cu / capi_h2c.cu / capi_gt.cu / capi_serial.cu against the mock CUDA runtime (tests/emul/mock) -> libemul_cabi.so"""
     so = os.path.join(_DIR, "libemul_cabi.so")
     stamp = so + ".stamp"
     dg = _digest("cabi")
@@ -47,6 +47,7 @@ def build_cabi():
               "-I", _CSRC, "-I", os.path.join(_ROOT, "include"), "-include", os.path.join(_DIR, "cuda_host_shim.h")]
     objs = []
     for src in (os.path.join(_CSRC, "capi_fr.cu"), os.path.join(_CSRC, "capi_h2c.cu"), os.path.join(_CSRC, "capi_gt.cu"),
+                os.path.join(_CSRC, "capi_serial.cu"),
                 os.path.join(_DIR, "emul_cabi_ctx.cpp")):
         obj = os.path.join(_DIR, os.path.basename(src) + ".emul.o")
         subprocess.check_call(common + ["-x", "c++", "-c", src, "-o", obj])

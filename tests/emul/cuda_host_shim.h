@@ -49,6 +49,18 @@ static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t s) {
 static inline int __clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
 static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
 static inline int __ffs(uint32_t x) { return __builtin_ffs((int)x); }
+// PRMT: result byte i = byte (selector nibble i & 7) of the 8 bytes {y, x}; bit 3 of a nibble (sign replication) unused here
+static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t sel) {
+  uint64_t v = ((uint64_t)y << 32) | x;
+  uint32_t r = 0;
+  for (int i = 0; i < 4; i++) {
+    uint32_t n = (sel >> (4 * i)) & 0xf;
+    uint32_t b = (uint32_t)(v >> (8 * (n & 7))) & 0xff;
+    if (n & 8) b = (b & 0x80) ? 0xff : 0x00;
+    r |= b << (8 * i);
+  }
+  return r;
+}
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 using std::min;
 using std::max;

@@ -131,3 +131,28 @@ def test_gt_mul(eng, orc):
     assert eng.gt_mul_batch(g[:0], s[:0]).shape == (0, 72)
     with pytest.raises(ValueError):
         eng.gt_mul_batch(g, s[:2])
+
+
+def test_serialization_units(eng, orc):
+    """capi_serial.cu (validated on hardware in round 1) through the mock runtime: the reference's golden .dat files
+    byte for byte, deserialization round trip and rejects, subgroup checks — a CPU regression net for later edits"""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "dat_vectors.npz"))
+    for k, G in ((1, orc.G1), (2, orc.G2)):
+        m = 40
+        gen = G.generator()
+        pts = [G.identity(1)]
+        for _ in range(m - 1):
+            pts.append(G.add(pts[-1], gen))
+        xy, inf = G.batch_normalize(np.concatenate(pts))
+        for compressed, name in ((True, "g%d_compressed" % k), (False, "g%d_uncompressed" % k)):
+            w = (48 if compressed else 96) * k
+            want = gold[name][:m * w].reshape(m, w)
+            got = eng.serialize(k, xy, inf, compressed=compressed)
+            assert np.array_equal(got, want)                                   # src/tests/mod.rs:3-76
+            dxy, dinf, st = eng.deserialize(k, want, compressed=compressed)
+            assert (st == 3).all() and np.array_equal(dinf, inf) and np.array_equal(dxy[inf == 0], xy[inf == 0])
+        assert (eng.check(k, xy, inf) == 3).all()
+        bad = gold["g%d_compressed" % k][:48 * k].copy().reshape(1, 48 * k)
+        bad[0, 0] &= 0x7f                                                      # compression flag cleared
+        assert eng.deserialize(k, bad, compressed=True)[2][0] & 1 == 0
