@@ -200,7 +200,12 @@ __global__ void __launch_bounds__(256) k_imad_peak(int iters, uint64_t *sink) {
 #pragma unroll
     for (int r = 0; r < 16; r++) {
 #pragma unroll
-      for (int k = 0; k < 8; k++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a + k), "r"(b + r));
+      for (int k = 0; k < 8; k++)
+#ifdef B200_HOST_EMUL  // CPU test harness: the same multiply-add in C
+        acc[k] += (uint64_t)(a + k) * (b + r);
+#else
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a + k), "r"(b + r));
+#endif
     }
   }
   uint64_t x = 0;
@@ -312,7 +317,7 @@ int b200_ctx_create(int device, b200_ctx **out) {
     cudaSetDevice(prev);
     return B200_ENOMEM;
   }
-  k_fp_inv_table_init<<<1, 32, 0, c->stream>>>(c->inv_pow2);
+  B200_KERNEL_LAUNCH(k_fp_inv_table_init, 1, 32, 0, c->stream, c->inv_pow2);
   if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
     b200_ctx_destroy(c);
     cudaSetDevice(prev);

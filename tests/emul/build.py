@@ -37,43 +37,29 @@ def build(variant="default"):
 
 
 def build_cabi():
-    """the host side of capi_fr.cu / capi_h2c.cu / capi_gt.cu / capi_serial.cu against the mock CUDA runtime (tests/emul/mock) -> libemul_cabi.so"""
+    """The HOST side of the C ABI against the mock CUDA runtime (tests/emul/mock): every unit except the MSM one (its
+    kernels use cp.async / match.any PTX) — capi_basic.cu (the real ctx, tuning, timing, tower / group / config-1
+    kernels), capi_pairing.cu + pairing_v4/v5/v6.cu, capi_serial.cu, capi_fr.cu, capi_h2c.cu, capi_gt.cu.  Every launch
+    runs on the fiber scheduler (fiber_warp.h), so warp- and block-cooperative kernels work.  -> libemul_cabi.so"""
     so = os.path.join(_DIR, "libemul_cabi.so")
     stamp = so + ".stamp"
-    dg = _digest("cabi")
+    dg = _digest("cabi_full")
     if os.path.exists(so) and os.path.exists(stamp) and open(stamp).read() == dg:
         return so
-    common = ["g++", "-O1", "-std=c++17", "-fPIC", "-pthread", "-Wno-unknown-pragmas", "-I", os.path.join(_DIR, "mock"), "-I", _DIR,
+    common = ["g++", "-O1", "-std=c++17", "-fPIC", "-pthread", "-Wno-unknown-pragmas", "-Wno-unused-variable",
+              "-DEMUL_LAUNCH_COOPERATIVE", "-DEMUL_DYNAMIC_SMEM_BYTES=65536", "-I", os.path.join(_DIR, "mock"), "-I", _DIR,
               "-I", _CSRC, "-I", os.path.join(_ROOT, "include"), "-include", os.path.join(_DIR, "cuda_host_shim.h")]
-    objs = []
-    for src in (os.path.join(_CSRC, "capi_fr.cu"), os.path.join(_CSRC, "capi_h2c.cu"), os.path.join(_CSRC, "capi_gt.cu"),
-                os.path.join(_CSRC, "capi_serial.cu"),
-                os.path.join(_DIR, "emul_cabi_ctx.cpp")):
-        obj = os.path.join(_DIR, os.path.basename(src) + ".emul.o")
-        subprocess.check_call(common + ["-x", "c++", "-c", src, "-o", obj])
-        objs.append(obj)
-    subprocess.check_call(["g++", "-shared", "-pthread", "-o", so] + objs)
-    open(stamp, "w").write(dg)
-    return so
+    units = ["capi_basic.cu", "capi_pairing.cu", "pairing_v4.cu", "pairing_v5.cu", "pairing_v6.cu", "capi_serial.cu",
+             "capi_fr.cu", "capi_h2c.cu", "capi_gt.cu"]
+    from concurrent.futures import ThreadPoolExecutor
 
+    def one(u):
+        obj = os.path.join(_DIR, u + ".emul.o")
+        subprocess.check_call(common + ["-x", "c++", "-c", os.path.join(_CSRC, u), "-o", obj])
+        return obj
 
-def build_cabi_pairing():
-    """capi_pairing.cu + pairing_v4/v5/v6.cu against the mock runtime, every launch on the fiber scheduler (the product
-    kernel uses __syncthreads and dynamic shared memory) -> libemul_cabi_pairing.so"""
-    so = os.path.join(_DIR, "libemul_cabi_pairing.so")
-    stamp = so + ".stamp"
-    dg = _digest("cabi_pairing")
-    if os.path.exists(so) and os.path.exists(stamp) and open(stamp).read() == dg:
-        return so
-    common = ["g++", "-O1", "-std=c++17", "-fPIC", "-pthread", "-Wno-unknown-pragmas", "-DEMUL_LAUNCH_COOPERATIVE",
-              "-DEMUL_DYNAMIC_SMEM_BYTES=40960", "-Wno-unused-variable", "-I", os.path.join(_DIR, "mock"), "-I", _DIR, "-I", _CSRC, "-I", os.path.join(_ROOT, "include"),
-              "-include", os.path.join(_DIR, "cuda_host_shim.h")]
-    objs = []
-    for src in [os.path.join(_CSRC, f) for f in ("capi_pairing.cu", "pairing_v4.cu", "pairing_v5.cu", "pairing_v6.cu")] + \
-            [os.path.join(_DIR, "emul_cabi_pairing_ctx.cpp")]:
-        obj = os.path.join(_DIR, os.path.basename(src) + ".emulp.o")
-        subprocess.check_call(common + ["-x", "c++", "-c", src, "-o", obj])
-        objs.append(obj)
+    with ThreadPoolExecutor(len(units)) as ex:
+        objs = list(ex.map(one, units))
     subprocess.check_call(["g++", "-shared", "-pthread", "-o", so] + objs)
     open(stamp, "w").write(dg)
     return so

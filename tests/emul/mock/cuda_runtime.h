@@ -34,10 +34,52 @@ static inline cudaError_t cudaGetDevice(int *d) {
   return cudaSuccess;
 }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+struct emul_event_rec {
+  double t_ms;
+};
+double emul_event_now_ms();
 static inline cudaError_t cudaEventCreate(cudaEvent_t *e) {
-  *e = nullptr;
+  *e = std::calloc(1, sizeof(emul_event_rec));
   return cudaSuccess;
 }
-static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t e) {
+  std::free(e);
+  return cudaSuccess;
+}
+static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) {
+  if (e) static_cast<emul_event_rec *>(e)->t_ms = emul_event_now_ms();
+  return cudaSuccess;
+}
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) {
+  *ms = (float)(static_cast<emul_event_rec *>(b)->t_ms - static_cast<emul_event_rec *>(a)->t_ms);
+  return cudaSuccess;
+}
 static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
 static inline const char *cudaGetErrorString(cudaError_t) { return "mock CUDA error"; }
+// ---- what capi_basic.cu needs on top: one "device", streams / events as opaque tokens, a wall clock for event times
+#include <chrono>
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
+struct cudaDeviceProp {
+  int multiProcessorCount;
+};
+static inline cudaError_t cudaGetDeviceCount(int *n) {
+  *n = 1;
+  return cudaSuccess;
+}
+static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
+  p->multiProcessorCount = 1;   // keeps the "batch larger than one wave" thresholds small on the CPU
+  return cudaSuccess;
+}
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) {
+  *s = std::malloc(1);
+  return cudaSuccess;
+}
+static inline cudaError_t cudaStreamDestroy(cudaStream_t s) {
+  std::free(s);
+  return cudaSuccess;
+}
+inline double emul_event_now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}

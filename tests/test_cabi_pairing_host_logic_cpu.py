@@ -16,7 +16,7 @@ from tests.emul import build as emul_build
 def eng():
     from bls12_381_b200 import _lib
     from bls12_381_b200.engine import Engine
-    lib = C.CDLL(emul_build.build_cabi_pairing())
+    lib = C.CDLL(emul_build.build_cabi())
     for name, args in _lib.SIGNATURES.items():
         if hasattr(lib, name):
             f = getattr(lib, name)
