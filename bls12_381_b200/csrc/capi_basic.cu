@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(128) k_batch_normalize(const char *p, size_t n
 // out = sum of n projective points: one block, tree in shared memory with complete adds
 template <class F>
 __global__ void __launch_bounds__(128) k_sum(const char *parts, size_t n, char *out) {
-  extern __shared__ char smem[];
+  B200_DYN_SMEM(char, smem);
   constexpr size_t PB = 3 * field_traits<F>::bytes;
   proj<F> acc = proj_identity<F>();
   for (size_t i = threadIdx.x; i < n; i += blockDim.x) acc = proj_add(acc, proj_load<F>(parts + PB * i));

@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(int nbuckets, size
     // software pipeline: the NEXT point of the bucket is copied global -> shared with cp.async (LDGSTS, no
     // registers held across the ~3000-instruction addition) while the current addition runs.  Double buffer,
     // 16-byte chunks interleaved across the block's threads (conflict-free LDS.128).
-    extern __shared__ uint4 pf[];
+    B200_DYN_SMEM(uint4, pf);
     constexpr int NCH = (int)(AB / 16);
     auto issue = [&](int buf, uint32_t e) {
       const char *src = points + AB * (size_t)(e & ENT_IDX);
@@ -225,11 +225,17 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(int nbuckets, size
       const char *srcx = (e & ENT_PHI) ? bx + FB * (size_t)(e & ENT_IDX) : src;
 #pragma unroll
       for (int c = 0; c < NCH; c++) {
-        unsigned dst = (unsigned)__cvta_generic_to_shared(&pf[(buf * NCH + c) * 128 + threadIdx.x]);
         const char *g = c < NCH / 2 ? srcx + 16 * c : src + 16 * c;
+#ifdef B200_HOST_EMUL  // CPU test harness: the copy is synchronous
+        pf[(buf * NCH + c) * 128 + threadIdx.x] = *reinterpret_cast<const uint4 *>(g);
+#else
+        unsigned dst = (unsigned)__cvta_generic_to_shared(&pf[(buf * NCH + c) * 128 + threadIdx.x]);
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g) : "memory");
+#endif
       }
+#ifndef B200_HOST_EMUL
       asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
     };
     uint32_t e = cnt ? __ldg(idx) : 0u;
     if (cnt) issue(0, e);
@@ -238,9 +244,11 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(int nbuckets, size
       if (t + 1 < cnt) {
         e_next = __ldg(idx + t + 1);
         issue((t + 1) & 1, e_next);
+#ifndef B200_HOST_EMUL
         asm volatile("cp.async.wait_group 1;" ::: "memory");
       } else {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
       }
       const uint4 *b = &pf[((t & 1) * NCH) * 128 + threadIdx.x];
       uint32_t w[AB / 4];
@@ -308,7 +316,7 @@ template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_msm_accumulate_g2sm(int nbuckets, size_t total, size_t slot0, const char *points,
                                                                  size_t sstride, const uint32_t *offsets, const uint32_t *hist,
                                                                  const uint32_t *sorted, const uint32_t *order, char *buckets) {
-  extern __shared__ uint32_t sm[];
+  B200_DYN_SMEM(uint32_t, sm);
   size_t t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (t0 >= total) return;
   size_t k = slot0 + order[t0];
@@ -363,7 +371,7 @@ __global__ void __launch_bounds__(128) k_msm_giant_parts(int nbuckets, size_t sl
                                                        const uint32_t *order, const char *points, const char *bx,
                                                        size_t sstride, const uint32_t *offsets, const uint32_t *hist,
                                                        const uint32_t *sorted, char *gparts, uint32_t max_giants) {
-  extern __shared__ char smem[];
+  B200_DYN_SMEM(char, smem);
   constexpr size_t FB = field_traits<F>::bytes, AB = 2 * FB, PB = 3 * FB;
   uint32_t ng = min(size_hist[SIZE_BINS - 1], max_giants);
   for (uint32_t item = blockIdx.x; item < ng * GIANT_PARTS; item += gridDim.x) {
@@ -447,7 +455,7 @@ __device__ proj<F> proj_mul_small(const proj<F> &p, uint32_t k) {
 // grid = (blocks_per_window, nloc).  Thread handles `chunk` consecutive buckets.
 template <class F, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_msm_reduce(int nbuckets, int chunk, const char *buckets, char *partials) {
-  extern __shared__ char smem[];
+  B200_DYN_SMEM(char, smem);
   constexpr size_t PB = 3 * field_traits<F>::bytes;
   int j = blockIdx.y;
   int t = blockIdx.x * BLOCK + threadIdx.x;       // chunk index within the window

@@ -129,10 +129,19 @@ inline void timing_end(b200_ctx *ctx, int r, cudaStream_t strm = nullptr) {
   if (r >= 0) cudaEventRecord(ctx->ev_pool[2 * r + 1], strm ? strm : ctx->stream);
 }
 
+// dynamic shared memory of a kernel: `extern __shared__ T name[];` — in the CPU test harness a pointer into one static
+// buffer (one block runs at a time there)
+#ifdef B200_HOST_EMUL
+#define B200_DYN_SMEM(type, name) type *name = reinterpret_cast<type *>(emul_dyn_smem)
+#else
+#define B200_DYN_SMEM(type, name) extern __shared__ type name[]
+#endif
+
 // the one place a kernel is launched from.  The CPU test harness (tests/emul/, B200_HOST_EMUL) compiles the host side of
 // the units with non-cooperative kernels against a mock runtime and turns a launch into a (block, thread) loop.
 #ifdef B200_HOST_EMUL
-#define B200_KERNEL_LAUNCH(kernel, grid, block, smem, strm, ...) emul_kernel_launch(kernel, grid, block, __VA_ARGS__)
+#define B200_KERNEL_LAUNCH(kernel, grid, block, smem, strm, ...) \
+  (emul_trace_launch(#kernel), emul_kernel_launch(kernel, grid, block, __VA_ARGS__))
 #else
 #define B200_KERNEL_LAUNCH(kernel, grid, block, smem, strm, ...) kernel<<<(grid), (block), (smem), (strm)>>>(__VA_ARGS__)
 #endif

@@ -37,19 +37,19 @@ def build(variant="default"):
 
 
 def build_cabi():
-    """The HOST side of the C ABI against the mock CUDA runtime (tests/emul/mock): every unit except the MSM one (its
-    kernels use cp.async / match.any PTX) — capi_basic.cu (the real ctx, tuning, timing, tower / group / config-1
-    kernels), capi_pairing.cu + pairing_v4/v5/v6.cu, capi_serial.cu, capi_fr.cu, capi_h2c.cu, capi_gt.cu.  Every launch
+    """The HOST side of the C ABI against the mock CUDA runtime (tests/emul/mock): every unit — capi_basic.cu (the real ctx, tuning, timing, tower / group / config-1
+    kernels), capi_pairing.cu + pairing_v4/v5/v6.cu, capi_serial.cu, capi_fr.cu, capi_h2c.cu, capi_gt.cu, capi_msm.cu (cp.async guarded in the
+    source, match.any / shuffles / atomics on the fiber scheduler).  Every launch
     runs on the fiber scheduler (fiber_warp.h), so warp- and block-cooperative kernels work.  -> libemul_cabi.so"""
     so = os.path.join(_DIR, "libemul_cabi.so")
     stamp = so + ".stamp"
     dg = _digest("cabi_full")
     if os.path.exists(so) and os.path.exists(stamp) and open(stamp).read() == dg:
         return so
-    common = ["g++", "-O1", "-std=c++17", "-fPIC", "-pthread", "-Wno-unknown-pragmas", "-Wno-unused-variable",
-              "-DEMUL_LAUNCH_COOPERATIVE", "-DEMUL_DYNAMIC_SMEM_BYTES=65536", "-I", os.path.join(_DIR, "mock"), "-I", _DIR,
+    common = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-pthread", "-Wno-unknown-pragmas", "-Wno-unused-variable",
+              "-DEMUL_LAUNCH_COOPERATIVE", "-I", os.path.join(_DIR, "mock"), "-I", _DIR,
               "-I", _CSRC, "-I", os.path.join(_ROOT, "include"), "-include", os.path.join(_DIR, "cuda_host_shim.h")]
-    units = ["capi_basic.cu", "capi_pairing.cu", "pairing_v4.cu", "pairing_v5.cu", "pairing_v6.cu", "capi_serial.cu",
+    units = ["capi_basic.cu", "capi_msm.cu", "capi_msm_lazy3.cu", "capi_pairing.cu", "pairing_v4.cu", "pairing_v5.cu", "pairing_v6.cu", "capi_serial.cu",
              "capi_fr.cu", "capi_h2c.cu", "capi_gt.cu"]
     from concurrent.futures import ThreadPoolExecutor
 

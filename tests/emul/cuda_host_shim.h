@@ -12,6 +12,8 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
+#include <cstdio>
+#include <cstdlib>
 #include <algorithm>   // all standard headers BEFORE the qualifier macros (libstdc++ uses __noinline__ itself)
 #include <vector>
 #include <thread>
@@ -24,7 +26,7 @@
 #define __forceinline__ inline
 #define __noinline__ __attribute__((noinline))
 #define __launch_bounds__(...)
-#define __shared__   /* only the `extern __shared__ T smem[];` form is supported: the harness defines `smem` */
+#define __shared__ static   /* static shared arrays: one block runs at a time; dynamic ones: B200_DYN_SMEM (ctx.cuh) */
 #define __restrict__
 
 struct uint4 {
@@ -34,7 +36,13 @@ static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
 struct emul_dim3 {
   unsigned x = 1, y = 1, z = 1;
 };
-static thread_local emul_dim3 threadIdx, blockIdx, blockDim, gridDim;
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+// `inline`: ONE instance per thread across all translation units of a library (inline device functions with external
+// linkage are merged by the linker and must see the same state as the kernel that calls them)
+inline thread_local emul_dim3 threadIdx, blockIdx, blockDim, gridDim;
 
 template <class T>
 static inline T __ldg(const T *p) { return *p; }
@@ -65,19 +73,46 @@ static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((ui
 using std::min;
 using std::max;
 
-#ifdef EMUL_DYNAMIC_SMEM_BYTES
-// `extern __shared__ char smem[];` inside a kernel of the translation unit's unnamed namespace names a member of that
-// namespace: define it here (this header is force-included first; all unnamed namespaces of a TU are one namespace)
-namespace {
-alignas(16) char smem[EMUL_DYNAMIC_SMEM_BYTES];
+// EMUL_TRACE=1 in the environment prints every kernel launch of the mock-runtime build to stderr and installs a SIGSEGV
+// handler that prints a backtrace (addresses resolvable with addr2line against the -g build of the library)
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+static inline void emul_segv_handler(int) {
+  void *bt[64];
+  int n = backtrace(bt, 64);
+  backtrace_symbols_fd(bt, n, 2);
+  _exit(139);
 }
+static inline void emul_trace_launch(const char *name) {
+  static const bool on = getenv("EMUL_TRACE") != nullptr;
+  static bool installed = false;
+  if (on && !installed) {
+    installed = true;
+    static char altstack[1 << 16];
+    stack_t ss;
+    ss.ss_sp = altstack;
+    ss.ss_size = sizeof(altstack);
+    ss.ss_flags = 0;
+    sigaltstack(&ss, nullptr);
+    struct sigaction sa;
+    memset(&sa, 0, sizeof(sa));
+    sa.sa_handler = emul_segv_handler;
+    sa.sa_flags = SA_ONSTACK;
+    sigaction(SIGSEGV, &sa, nullptr);
+  }
+  if (on) fprintf(stderr, "[emul] launch %s\n", name);
+}
+#ifndef EMUL_DYNAMIC_SMEM_BYTES
+#define EMUL_DYNAMIC_SMEM_BYTES (256 * 1024)
 #endif
+alignas(16) inline char emul_dyn_smem[EMUL_DYNAMIC_SMEM_BYTES];   // what B200_DYN_SMEM points at
 #ifdef EMUL_LAUNCH_COOPERATIVE
 // every launch goes through the fiber scheduler of fiber_warp.h (kernels with __syncthreads / shuffles / shared memory)
 #include "fiber_warp.h"
 template <class K, class... A>
-static inline void emul_kernel_launch(K k, unsigned grid, unsigned block, A... a) {
-  emul_cooperative_launch(k, grid, block, a...);
+static inline void emul_kernel_launch(K k, dim3 grid, dim3 block, A... a) {
+  emul_cooperative_launch(k, grid, block.x, a...);
 }
 #else
 // a kernel "launch": every (block, thread) in turn on the calling host thread.  Only valid for kernels without

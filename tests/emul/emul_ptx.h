@@ -3,7 +3,7 @@
 #pragma once
 #include <cstdint>
 // (included from inside namespace b200)
-static thread_local uint32_t emul_cf = 0;
+inline thread_local uint32_t emul_cf = 0;   // one CC.CF per host thread, shared by all translation units
 #define EMUL_DEV static inline
 EMUL_DEV void ptx_add_cc(uint32_t &d, uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b; d = (uint32_t)t; emul_cf = (uint32_t)(t >> 32); }
 EMUL_DEV void ptx_addc_cc(uint32_t &d, uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b + emul_cf; d = (uint32_t)t; emul_cf = (uint32_t)(t >> 32); }

@@ -13,7 +13,7 @@
 #include <vector>
 
 struct emul_fiber_block {
-  static constexpr size_t STACK = 512 * 1024;
+  static constexpr size_t STACK = 256 * 1024;
   unsigned nthreads = 0;
   std::vector<ucontext_t> ctx;
   std::vector<char *> stacks;
@@ -28,7 +28,7 @@ struct emul_fiber_block {
   std::vector<unsigned long long> xchg;  // [warp][32]
   unsigned long long progress = 0;
 };
-static thread_local emul_fiber_block *emul_blk = nullptr;
+inline thread_local emul_fiber_block *emul_blk = nullptr;   // ONE instance per thread across translation units
 
 static inline void emul_yield() {
   emul_fiber_block *b = emul_blk;
@@ -98,6 +98,29 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
   emul_warp_barrier();
   return r;
 }
+// lanes of the calling warp that have not exited
+static inline unsigned __activemask() {
+  emul_fiber_block *b = emul_blk;
+  unsigned w = b->cur >> 5, m = 0;
+  for (unsigned l = 0; l < 32; l++)
+    if (32 * w + l < b->nthreads && !b->done[32 * w + l]) m |= 1u << l;
+  return m;
+}
+// mask of the live lanes whose value equals the caller's (all live lanes of the warp must call)
+template <class T>
+static inline unsigned __match_any_sync(unsigned, T v) {
+  emul_fiber_block *b = emul_blk;
+  unsigned w = b->cur >> 5, lane = b->cur & 31;
+  unsigned long long bits = 0;
+  memcpy(&bits, &v, sizeof(T));
+  b->xchg[32 * w + lane] = bits;
+  emul_warp_barrier();
+  unsigned r = 0;
+  for (unsigned l = 0; l < 32; l++)
+    if (32 * w + l < b->nthreads && !b->done[32 * w + l] && b->xchg[32 * w + l] == bits) r |= 1u << l;
+  emul_warp_barrier();
+  return r;
+}
 static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 static inline int __all_sync(unsigned m, int pred) {
   emul_fiber_block *b = emul_blk;
@@ -135,7 +158,8 @@ static void emul_fiber_main() {
 }
 
 // run ONE block of `block` threads cooperatively; `call()` invokes the kernel body with its arguments
-static inline void emul_run_block_cooperative(unsigned block, unsigned block_index, unsigned grid, std::function<void()> call) {
+static inline void emul_run_block_cooperative(unsigned block, emul_dim3 block_index, emul_dim3 grid, std::function<void()> call,
+                                              std::vector<char *> *stack_pool = nullptr) {
   emul_fiber_block b;
   b.nthreads = block;
   b.live = block;
@@ -151,7 +175,7 @@ static inline void emul_run_block_cooperative(unsigned block, unsigned block_ind
   b.body = call;
   emul_blk = &b;
   for (unsigned t = 0; t < block; t++) {
-    b.stacks[t] = (char *)malloc(emul_fiber_block::STACK);
+    b.stacks[t] = stack_pool ? (*stack_pool)[t] : (char *)malloc(emul_fiber_block::STACK);
     getcontext(&b.ctx[t]);
     b.ctx[t].uc_stack.ss_sp = b.stacks[t];
     b.ctx[t].uc_stack.ss_size = emul_fiber_block::STACK;
@@ -159,8 +183,8 @@ static inline void emul_run_block_cooperative(unsigned block, unsigned block_ind
     makecontext(&b.ctx[t], emul_fiber_main, 0);
   }
   blockDim = emul_dim3{block, 1, 1};
-  gridDim = emul_dim3{grid, 1, 1};
-  blockIdx = emul_dim3{block_index, 0, 0};
+  gridDim = grid;
+  blockIdx = block_index;
   while (b.live) {
     unsigned long long before = b.progress;
     for (unsigned t = 0; t < block; t++) {
@@ -174,10 +198,16 @@ static inline void emul_run_block_cooperative(unsigned block, unsigned block_ind
       abort();
     }
   }
-  for (unsigned t = 0; t < block; t++) free(b.stacks[t]);
+  if (!stack_pool)
+    for (unsigned t = 0; t < block; t++) free(b.stacks[t]);
   emul_blk = nullptr;
 }
 template <class K, class... A>
-static inline void emul_cooperative_launch(K k, unsigned grid, unsigned block, A... a) {
-  for (unsigned bi = 0; bi < grid; bi++) emul_run_block_cooperative(block, bi, grid, [=]() { k(a...); });
+static inline void emul_cooperative_launch(K k, dim3 grid, unsigned block, A... a) {
+  std::vector<char *> pool(block);
+  for (unsigned t = 0; t < block; t++) pool[t] = (char *)malloc(emul_fiber_block::STACK);
+  for (unsigned by = 0; by < grid.y; by++)
+    for (unsigned bx = 0; bx < grid.x; bx++)
+      emul_run_block_cooperative(block, emul_dim3{bx, by, 0}, emul_dim3{grid.x, grid.y, 1}, [=]() { k(a...); }, &pool);
+  for (unsigned t = 0; t < block; t++) free(pool[t]);
 }

@@ -27,6 +27,10 @@ static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cuda
   std::memmove(d, s, n);
   return cudaSuccess;
 }
+static inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) {
+  std::memset(d, v, n);
+  return cudaSuccess;
+}
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int *d) {

@@ -1,7 +1,6 @@
 """The bodies of the hardware-validated parity tests (tests/test_gpu_parity.py) replayed on the CPU: the real C ABI units
 compiled with g++ against the mock CUDA runtime (tests/emul/: same device source, bit-exact PTX carry models, fiber
-scheduler for cooperative kernels) behind the real Engine class.  The MSM unit is not in the mock library (its kernels
-use cp.async / match.any PTX), so MSM tests stay GPU-only; the golden-file serialization test (1000 warp-cooperative
+scheduler for cooperative kernels) behind the real Engine class.  MSM has its own file (tests/test_msm_on_mock_cpu.py); the golden-file serialization test (1000 warp-cooperative
 scalar multiplications to build its inputs) is too slow on the fiber scheduler — tests/test_cabi_host_logic_cpu.py has a
 smaller one — and the G2Prepared test needs torch CUDA tensors.  Purpose: a regression net for edits made without a GPU —
 these tests were green on a B200 in round 1; if one turns red here, the edit changed behaviour."""

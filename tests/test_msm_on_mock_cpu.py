@@ -1,0 +1,127 @@
+"""The MSM unit (capi_msm.cu: digit extraction, counting sort, bucket scheduling, bucket accumulation with its prefetch
+pipeline, giant-bucket split, bucket reduction, warp-cooperative Horner, GLV, batched-affine levels, window sharding) and
+its experimental second build (capi_msm_lazy3.cu) on the CPU: compiled with g++ against the mock CUDA runtime, every
+kernel on the fiber scheduler (match.any, shuffles, atomics, shared memory, barriers), driven through the real C ABI and
+the real Engine class — against the oracle.  Sizes are tiny (one emulated MSM costs ~2 s, mostly the 256-doubling Horner
+chain on the fiber scheduler); the hardware-validated tests at real sizes are tests/test_gpu_parity.py and
+tests/test_gpu_fullsize.py.  Purpose: a regression net for MSM edits made without a GPU."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import tests.test_gpu_parity as GP
+from tests import pyref, util
+from tests.emul import build as emul_build
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from bls12_381_b200 import _lib
+    from bls12_381_b200.engine import Engine
+    lib = C.CDLL(emul_build.build_cabi())
+    for name, args in _lib.SIGNATURES.items():
+        if hasattr(lib, name):
+            f = getattr(lib, name)
+            f.argtypes = args
+            f.restype = _lib._RESTYPE.get(name, C.c_int)
+
+    class MockEngine(Engine):
+        def __init__(self):
+            self.lib = lib
+            h = C.c_void_p()
+            assert lib.b200_ctx_create(-1, C.byref(h)) == 0
+            self.h = h
+
+    e = MockEngine()
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def data(orc):
+    rng = np.random.default_rng(18100)
+    out = {}
+    for k in (1, 2):
+        _, xy, inf = util.rand_points(orc, k, rng, 64)
+        out[k] = (xy, inf, util.rand_scalars(rng, 64))
+    return out
+
+
+def _edge_set(orc, k, xy, inf, s, n):
+    xy2, inf2, s2 = xy[:n].copy(), inf[:n].copy(), s[:n].copy()
+    w = 6 * k
+    s2[0] = 0
+    s2[1] = util.scalar_bytes(pyref.Q - 1)
+    s2[2] = util.scalar_bytes(1)
+    inf2[3] = 1
+    xy2[5], s2[5] = xy2[4], s2[4]                    # P + P in a bucket
+    xy2[7] = xy2[6]
+    xy2[7, w:] = orc.tower(k, "neg", xy2[6, w:])
+    s2[7] = s2[6]                                    # P + (-P) in a bucket
+    s2[8:n] = s2[8]                                  # one crowded bucket per window
+    return xy2, inf2, s2
+
+
+def test_g1_msm_sizes_and_edges(eng, orc, data):
+    xy, inf, s = data[1]
+    G = orc.G1
+    assert G.to_affine(eng.msm(1, xy[:0], None, s[:0]))[1][0] == 1                       # n = 0 -> identity
+    GP._msm_case(eng, orc, 1, xy[:1], inf[:1], s[:1], cs=(0, 7))
+    GP._msm_case(eng, orc, 1, xy[:37], inf[:37], s[:37], cs=(0,))
+    GP._msm_case(eng, orc, 1, *_edge_set(orc, 1, xy, inf, s, 64), cs=(0, 8))
+    both = np.concatenate([xy[:4], xy[:4]])
+    both[4:, 6:] = orc.tower(1, "neg", xy[:4, 6:])
+    assert G.to_affine(eng.msm(1, both, None, np.concatenate([s[:4], s[:4]])))[1][0] == 1   # everything cancels
+
+
+@pytest.mark.parametrize("mode", [4, 2, 3])
+def test_g2_msm_and_bucket_kernel_variants(eng, orc, data, mode):
+    xy, inf, s = data[2]
+    eng.set_tuning("g2_acc_blocks", mode)
+    try:
+        GP._msm_case(eng, orc, 2, *_edge_set(orc, 2, xy, inf, s, 24), cs=(6,))
+        if mode == 4:
+            GP._msm_case(eng, orc, 2, xy[:5], inf[:5], s[:5], cs=(0,))
+    finally:
+        eng.set_tuning("g2_acc_blocks", 4)
+
+
+def test_glv_prefetch_and_affine_levels(eng, orc, data):
+    xy, inf, s = data[1]
+    case = _edge_set(orc, 1, xy, inf, s, 40)
+    for key, val, back in (("g1_glv", 1, 0), ("g1_prefetch", 0, 1), ("msm_affine_levels", 2, 0)):
+        eng.set_tuning(key, val)
+        try:
+            GP._msm_case(eng, orc, 1, *case, cs=(5,))
+        finally:
+            eng.set_tuning(key, back)
+
+
+def test_window_sharding_and_sum(eng, orc, data):
+    """b200_g1_msm_shard_dev for both shards of a 2-way split + b200_g1_sum_dev == the full MSM ("device" pointers are host
+    pointers under the mock runtime)"""
+    xy, inf, s = data[1]
+    n = 30
+    parts = np.zeros((2, 18), np.uint64)
+    for shard in (0, 1):
+        rc = eng.lib.b200_g1_msm_shard_dev(eng.h, xy.ctypes.data, inf.ctypes.data, s.ctypes.data, n, shard, 2,
+                                           parts[shard:shard + 1].ctypes.data)
+        assert rc == 0
+    out = np.zeros((1, 18), np.uint64)
+    assert eng.lib.b200_g1_sum_dev(eng.h, parts.ctypes.data, 2, out.ctypes.data) == 0
+    want = orc.G1.msm_naive(xy[:n], inf[:n], s[:n], threads=4)
+    assert np.array_equal(orc.G1.to_affine(out)[0], orc.G1.to_affine(want)[0])
+
+
+def test_experimental_lazy3_build_agrees(eng, orc, data):
+    """capi_msm_lazy3.cu (row-alternated lazy Fp2 multiply) through its own entry point"""
+    xy, inf, s = data[2]
+    case = _edge_set(orc, 2, xy, inf, s, 24)
+    f = eng.lib.b200x_lazy3_g2_msm
+    f.argtypes = [C.c_void_p] * 4 + [C.c_size_t, C.c_void_p]
+    f.restype = C.c_int
+    out = np.empty((1, 36), np.uint64)
+    assert f(eng.h, case[0].ctypes.data, case[1].ctypes.data, case[2].ctypes.data, 24, out.ctypes.data) == 0
+    want = orc.G2.msm_naive(*case, threads=4)
+    assert np.array_equal(orc.G2.to_affine(out)[0], orc.G2.to_affine(want)[0])
