@@ -16,8 +16,8 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libbls12381_b200.so")
 OBJ = os.path.join(HERE, "build")
 # (source, extra nvcc flags).  The pairing kernels have their own unit with their own Fp2-multiply variant (fp2.cuh).
-UNITS = [("capi_basic.cu", []), ("capi_pairing.cu", []), ("capi_msm.cu", []), ("capi_msm_lazy3.cu", []), ("capi_serial.cu", []),
-         ("pairing_v4.cu", []), ("pairing_v5.cu", []), ("pairing_v6.cu", []), ("capi_fr.cu", []), ("capi_h2c.cu", []), ("capi_gt.cu", [])]
+UNITS = [("capi_basic.cu", []), ("capi_pairing.cu", []), ("capi_msm.cu", []), ("capi_serial.cu", []),
+         ("pairing_v4.cu", []), ("pairing_coop.cu", []), ("capi_fr.cu", []), ("capi_h2c.cu", []), ("capi_gt.cu", [])]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

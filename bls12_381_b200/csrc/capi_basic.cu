@@ -394,8 +394,11 @@ int b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int value) {
   } else if (!strcmp(key, "g1_prefetch")) {
     ctx->tune_g1_prefetch = value != 0;
   } else if (!strcmp(key, "pairing_variant")) {
-    if (value < 4 || value > 6) return B200_EINVAL;
+    if (value != 4 && value != 7) return B200_EINVAL;  // 4 = one thread per pairing (pairing_v4.cu), 7 = six lanes per pairing
     ctx->tune_pairing_variant = value;
+  } else if (!strcmp(key, "coop_warps")) {
+    if (value < 1 || value > 16) return B200_EINVAL;
+    ctx->tune_coop_warps = value;
   } else if (!strcmp(key, "pairing_chunks")) {
     if (value < 1 || value > 64) return B200_EINVAL;
     ctx->tune_pairing_chunks = value;

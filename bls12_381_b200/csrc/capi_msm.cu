@@ -19,6 +19,9 @@
 // Steps 5-6 use the reference's COMPLETE formulas (curve.cuh); step 4's exceptional cases (duplicate points,
 // P + (-P)) are branched on explicitly; identity inputs and zero digits never reach a bucket.  Window sharding (shard, n_shards) restricts
 // steps 1-5 to windows w = shard (mod n_shards); step 6 then yields sum_{w in shard} 2^(cw) S_w.
+// Fp2 multiply of this unit: lazy reduction with row-alternated products / reductions (fp2.cuh; measured best for the
+// G2 bucket kernel in round 2: 30.1 vs 31.3 ms at 2^20)
+#define B200_FP2_LAZY3 1
 #include "ctx.cuh"
 #include "curve.cuh"
 #include "curve_warp.cuh"

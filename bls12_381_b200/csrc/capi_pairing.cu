@@ -14,23 +14,34 @@ using namespace b200;
   int b200_pair_miller_prepared_##v(b200_ctx *, cudaStream_t, const void *, const void *, const void *, const void *,  \
                                     size_t, void *);
 DECL_VARIANT(v4)
-DECL_VARIANT(v5)
-DECL_VARIANT(v6)
+// pairing_coop.cu: flags 1 = Miller loop over prepared coefficients, 2 = final exponentiation (of `in` when bit 0 is clear)
+int b200_pair_coop_launch(b200_ctx *, cudaStream_t, int flags, const void *p, const void *pi, const void *coeffs,
+                          const void *qi, const void *in, size_t n, void *out);
 
 namespace {
 
 // The pairing kernels live in their own translation unit (pairing_v4.cu: 255 registers, 4 resident 64-thread blocks
 // per SM, Fp2 multiply = Karatsuba over fp_mul_c calls).  Lower register budgets (168 / 128) and the inlined /
 // lazily reduced Fp2 multiplies were built the same way, measured slower, and removed.
+// variant 7: G2 line coefficients of all pairs (68 x 288 B each) into the scratch arena, then the six-lane Miller loop
+// (+ final exponentiation when `with_final_exp`) in ONE kernel
+int coop_from_affine(b200_ctx *ctx, cudaStream_t st, const void *p, const void *pi, const void *q, const void *qi, size_t n,
+                     void *out, bool with_final_exp) {
+  if (n == 0) return B200_OK;
+  int rc = arena_reserve(ctx, (size_t)19584 * n + 256);
+  if (rc != B200_OK) return rc;
+  char *co = arena_take<char>(ctx, (size_t)19584 * n);
+  rc = b200_pair_g2_prepare_v4(ctx, st, q, qi, n, co);
+  if (rc != B200_OK) return rc;
+  return b200_pair_coop_launch(ctx, st, with_final_exp ? 3 : 1, p, pi, co, qi, nullptr, n, out);
+}
 int miller_on(b200_ctx *ctx, cudaStream_t st, const void *p, const void *pi, const void *q, const void *qi, size_t n,
               void *out) {
-  if (ctx->tune_pairing_variant == 5) return b200_pair_miller_v5(ctx, st, p, pi, q, qi, n, out);  // experimental (pairing_v5.cu)
-  if (ctx->tune_pairing_variant == 6) return b200_pair_miller_v6(ctx, st, p, pi, q, qi, n, out);  // experimental (pairing_v6.cu)
+  if (ctx->tune_pairing_variant == 7) return coop_from_affine(ctx, st, p, pi, q, qi, n, out, false);
   return b200_pair_miller_v4(ctx, st, p, pi, q, qi, n, out);
 }
 int final_exp_on(b200_ctx *ctx, cudaStream_t st, const void *in, size_t n, void *out) {
-  if (ctx->tune_pairing_variant == 5) return b200_pair_final_exp_v5(ctx, st, in, n, out);
-  if (ctx->tune_pairing_variant == 6) return b200_pair_final_exp_v6(ctx, st, in, n, out);
+  if (ctx->tune_pairing_variant == 7) return b200_pair_coop_launch(ctx, st, 2, nullptr, nullptr, nullptr, nullptr, in, n, out);
   return b200_pair_final_exp_v4(ctx, st, in, n, out);
 }
 int miller_dev(b200_ctx *ctx, const void *p, const void *pi, const void *q, const void *qi, size_t n, void *out) {
@@ -43,6 +54,7 @@ int final_exp_dev(b200_ctx *ctx, const void *in, size_t n, void *out) { return f
 // whole extra wave for the last, partially filled one (2^16 pairs = 1.73 waves of 148 SMs x 4 x 64 threads);
 // with independent chunks in flight the block scheduler back-fills the tail of one kernel with blocks of another.
 int pairing_dev(b200_ctx *ctx, const void *p, const void *pi, const void *q, const void *qi, size_t n, void *out) {
+  if (ctx->tune_pairing_variant == 7) return coop_from_affine(ctx, ctx->stream, p, pi, q, qi, n, out, true);
   int chunks = ctx->tune_pairing_chunks;
   if (chunks < 1) chunks = 1;
   // chunking only pays when the batch exceeds one wave of resident threads (148 SMs x 4 blocks x 64 = 37 888): below
@@ -143,7 +155,8 @@ int b200_miller_loop_prepared_batch_dev(b200_ctx *ctx, const void *p, const void
                                         const void *q_inf, size_t n, void *out) {
   CHECK_CTX(ctx);
   if (n && (!p || !coeffs || !out)) return B200_EINVAL;
-  int rc = b200_pair_miller_prepared_v4(ctx, ctx->stream, p, p_inf, coeffs, q_inf, n, out);
+  int rc = ctx->tune_pairing_variant == 7 ? b200_pair_coop_launch(ctx, ctx->stream, 1, p, p_inf, coeffs, q_inf, nullptr, n, out)
+                                          : b200_pair_miller_prepared_v4(ctx, ctx->stream, p, p_inf, coeffs, q_inf, n, out);
   return rc != B200_OK ? rc : sync(ctx);
 }
 int b200_g2_prepare(b200_ctx *ctx, const b200_g2_affine *q, const uint8_t *q_inf, size_t n, b200_fp2 *coeffs) {
@@ -176,7 +189,8 @@ int b200_multi_miller_loop_prepared(b200_ctx *ctx, const b200_g1_affine *p, cons
     if (q_inf) B200_CUDA(ctx, cudaMemcpyAsync(dqi, q_inf, n, cudaMemcpyHostToDevice, ctx->stream));
     B200_CUDA(ctx, cudaMemcpyAsync(dc, coeffs, 19584 * n, cudaMemcpyHostToDevice, ctx->stream));
   }
-  rc = b200_pair_miller_prepared_v4(ctx, ctx->stream, dp, dpi, dc, dqi, n, dml);
+  rc = ctx->tune_pairing_variant == 7 ? b200_pair_coop_launch(ctx, ctx->stream, 1, dp, dpi, dc, dqi, nullptr, n, dml)
+                                      : b200_pair_miller_prepared_v4(ctx, ctx->stream, dp, dpi, dc, dqi, n, dml);
   if (rc == B200_OK) rc = product_dev(ctx, dml, n, dout);
   if (rc != B200_OK) return rc;
   B200_CUDA(ctx, cudaMemcpyAsync(out, dout, 576, cudaMemcpyDeviceToHost, ctx->stream));

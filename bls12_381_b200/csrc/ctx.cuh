@@ -53,9 +53,12 @@ struct b200_ctx {
   // scalar-field NTT tables of capi_fr.cu (twiddles + coset powers for the last log_n used); freed by ctx_destroy
   void *fr_state = nullptr;
   void (*fr_state_free)(void *) = nullptr;
-  // Miller loop / final exponentiation kernels: 4 = pairing_v4.cu (validated, default), 5 = pairing_v5.cu / 6 =
-  // pairing_v6.cu (experimental dual- / triple-stream Fp2 multiply; CPU-validated, to be measured in round 2)
-  int tune_pairing_variant = 4;
+  // Miller loop / final exponentiation kernels: 4 = pairing_v4.cu, one thread per pairing (round 1).  The dual- / triple-
+  // stream Fp2-multiply builds (v5 / v6) measured slower on B200 (63.5 / 67.4 vs 59.3 ms at 2^16 pairs) and were removed.
+  // 7 = pairing_coop.cu: six lanes per pairing, Fp12 distributed over the lanes (round 2; default)
+  int tune_pairing_variant = 7;
+  int tune_coop_warps = 12;          // warps per block (one block per SM) of the lane-cooperative pairing kernels, 1..16
+  bool coop_attr_done = false;       // cudaFuncSetAttribute(max dynamic shared memory) done on this device
 };
 
 namespace b200 {

@@ -190,8 +190,7 @@ static __device__ __noinline__ fp fp_mul_c(fp a, fp b) { return fp_mul(a, b); }
 // next to each other (a whole chain at a time: PTX has a single CC.CF, so chains cannot be interleaved instruction by
 // instruction in the source — ptxas renames the carries into predicate registers and overlaps adjacent independent
 // chains) gives the scheduler two independent streams per warp.  Same values as two fp_mul calls.
-// EXPERIMENTAL (round 2 candidate): used only by the B200_FP2_KDUAL variant of fp2.cuh / pairing_v5.cu; CPU-validated,
-// not yet measured.
+// Used by the squaring of the B200_FP2_LAZY3 variant (fp2.cuh).
 struct fp_pair {
   fp r0, r1;
 };
@@ -247,52 +246,6 @@ B200_DEV fp_pair fp_mul_dual(const fp &a, const fp &b, const fp &c, const fp &d)
   }
   return fp_pair{fp_mul_tail(ev0, od0), fp_mul_tail(ev1, od1)};
 }
-static __device__ __noinline__ fp_pair fp_mul2_c(fp a, fp b, fp c, fp d) { return fp_mul_dual(a, b, c, d); }
-// THREE products with alternated rows (a*b, c*d, e*f): the whole Karatsuba Fp2 multiplication as one routine
-// (B200_FP2_KTRIPLE, pairing_v6.cu).  EXPERIMENTAL, same status as fp_mul_dual.
-struct fp_triple {
-  fp r0, r1, r2;
-};
-B200_DEV fp_triple fp_mul_triple(const fp &a, const fp &b, const fp &c, const fp &d, const fp &e, const fp &f) {
-  uint32_t ev0[12], od0[12], ev1[12], od1[12], ev2[12], od2[12];
-#pragma unroll
-  for (int j = 0; j < 12; j += 2) {
-    ptx_mul_lo(ev0[j], a.v[j], b.v[0]);
-    ptx_mul_hi(ev0[j + 1], a.v[j], b.v[0]);
-    ptx_mul_lo(od0[j], a.v[j + 1], b.v[0]);
-    ptx_mul_hi(od0[j + 1], a.v[j + 1], b.v[0]);
-    ptx_mul_lo(ev1[j], c.v[j], d.v[0]);
-    ptx_mul_hi(ev1[j + 1], c.v[j], d.v[0]);
-    ptx_mul_lo(od1[j], c.v[j + 1], d.v[0]);
-    ptx_mul_hi(od1[j + 1], c.v[j + 1], d.v[0]);
-    ptx_mul_lo(ev2[j], e.v[j], f.v[0]);
-    ptx_mul_hi(ev2[j + 1], e.v[j], f.v[0]);
-    ptx_mul_lo(od2[j], e.v[j + 1], f.v[0]);
-    ptx_mul_hi(od2[j + 1], e.v[j + 1], f.v[0]);
-  }
-  fp_redc_step(ev0, od0);
-  fp_redc_step(ev1, od1);
-  fp_redc_step(ev2, od2);
-#pragma unroll
-  for (int i = 1; i < 12; i += 2) {
-    fp_mul_row_acc(od0, ev0, a, b.v[i]);
-    fp_mul_row_acc(od1, ev1, c, d.v[i]);
-    fp_mul_row_acc(od2, ev2, e, f.v[i]);
-    fp_redc_step(od0, ev0);
-    fp_redc_step(od1, ev1);
-    fp_redc_step(od2, ev2);
-    if (i + 1 < 12) {
-      fp_mul_row_acc(ev0, od0, a, b.v[i + 1]);
-      fp_mul_row_acc(ev1, od1, c, d.v[i + 1]);
-      fp_mul_row_acc(ev2, od2, e, f.v[i + 1]);
-      fp_redc_step(ev0, od0);
-      fp_redc_step(ev1, od1);
-      fp_redc_step(ev2, od2);
-    }
-  }
-  return fp_triple{fp_mul_tail(ev0, od0), fp_mul_tail(ev1, od1), fp_mul_tail(ev2, od2)};
-}
-
 // ---------------------------------------------------------------------------------------------------
 // Lazy reduction support (used by the Fp2 multiplication): an unreduced 768-bit product, its Montgomery
 // reduction, and plain (non-modular) 384/768-bit add/sub.  Karatsuba Fp2 mul = 3 wide products (3 x 144
@@ -486,8 +439,7 @@ B200_DEV fpw fp_sqr_wide(const fp &a) {
   }
   return t;
 }
-// Row-alternated versions of the lazy-reduction building blocks (EXPERIMENTAL, round 2 candidate for the G2 bucket
-// kernel, which sits at 65 % of the multiplier with the plain versions; used only by B200_FP2_LAZY3): three unreduced
+// Row-alternated versions of the lazy-reduction building blocks (B200_FP2_LAZY3, the MSM unit's Fp2 multiply): three unreduced
 // products with their rows alternated, and two Montgomery reductions with their steps alternated.
 struct fpw3 {
   fpw w0, w1, w2;

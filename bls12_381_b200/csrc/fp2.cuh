@@ -61,8 +61,8 @@ B200_DEV void fp2_store(void *p, const fp2 &a) {
 // 0-byte frame), and the three/two Fp products inside are calls into the single fp_mul_c body.
 // Everything at Fp2 level and above (G2, Fp6, Fp12, pairing) goes through these.
 #define B200_NOINL static __device__ __noinline__
-// Three implementations of the called Fp2 multiply, chosen per translation unit (all return the same
-// canonical element, bit-identical to src/fp2.rs:205-222; measured on B200, round 1):
+// Implementations of the called Fp2 multiply, chosen per translation unit (all return the same
+// canonical element, bit-identical to src/fp2.rs:205-222; measured on B200, rounds 1-2):
 //   default            Karatsuba with LAZY reduction: three unreduced 768-bit products, two Montgomery
 //                      reductions (753 IMAD instead of 915).  Best where the IMAD pipe is saturated
 //                      (G2 MSM bucket kernel: -6 % time).  c0 = a0 b0 - a1 b1 (+ p 2^384 if negative),
@@ -70,9 +70,9 @@ B200_DEV void fp2_store(void *p, const fp2 &a) {
 //   B200_FP2_KCALL     Karatsuba over three calls of fp_mul_c: shortest dependent chains; best for the
 //                      latency-bound pairing kernels (2 warps per SMSP), where the lazy variant is 9 % slower.
 //   B200_FP2_KINLINE   Karatsuba with the three/two Fp products inlined side by side (more ILP for ptxas).
-//   B200_FP2_KDUAL     EXPERIMENTAL: two of the products in one row-alternating routine (fp_mul_dual) — not measured yet.
-//   B200_FP2_KTRIPLE   EXPERIMENTAL: all three in one routine (fp_mul_triple) — not measured yet.
-//   B200_FP2_LAZY3     EXPERIMENTAL: the lazy variant with row-alternated wide products / reductions — not measured yet.
+//   B200_FP2_LAZY3     the lazy variant with its three wide products and two reductions row-alternated: the MSM unit's
+//                      choice (G2 MSM 2^20: 30.1 vs 31.3 ms, round 2).  Row-alternated Karatsuba products inside the
+//                      pairing kernels (dual / triple streams) measured SLOWER (63.5 / 67.4 vs 59.3 ms) and were removed.
 #if defined(B200_FP2_KCALL)
 B200_NOINL fp2 fp2_mul_c(fp2 a, fp2 b) {
   fp t0 = fp_mul_c(a.c0, b.c0);
@@ -84,38 +84,13 @@ B200_NOINL fp2 fp2_sqr_c(fp2 a) {
   fp s = fp_add(a.c0, a.c1), d = fp_sub(a.c0, a.c1), t = fp_dbl(a.c0);
   return fp2{fp_mul_c(s, d), fp_mul_c(t, a.c1)};
 }
-#elif defined(B200_FP2_KDUAL)
-// EXPERIMENTAL (pairing_v5.cu): Karatsuba with the two independent products a0*b0, a1*b1 computed by ONE call whose
-// rows alternate (fp_mul_dual) — two dependent streams per warp instead of one; the squaring's two products likewise.
-B200_NOINL fp2 fp2_mul_c(fp2 a, fp2 b) {
-  fp_pair t = fp_mul2_c(a.c0, b.c0, a.c1, b.c1);
-  fp s = fp_mul_c(fp_add(a.c0, a.c1), fp_add(b.c0, b.c1));
-  return fp2{fp_sub(t.r0, t.r1), fp_sub(fp_sub(s, t.r0), t.r1)};
-}
-B200_NOINL fp2 fp2_sqr_c(fp2 a) {
-  fp s = fp_add(a.c0, a.c1), d = fp_sub(a.c0, a.c1), t = fp_dbl(a.c0);
-  fp_pair p = fp_mul2_c(s, d, t, a.c1);
-  return fp2{p.r0, p.r1};
-}
 #elif defined(B200_FP2_LAZY3)
-// EXPERIMENTAL: the default lazy-reduction multiply with its three wide products and its two reductions row-alternated
-// (fp_mul_wide_triple, fp_redc_wide_dual) — candidate for the G2 bucket kernel (65 % of the multiplier in round 1).
+// the lazy-reduction multiply with its three wide products and its two reductions row-alternated
+// (fp_mul_wide_triple, fp_redc_wide_dual): used by the MSM unit (G2 bucket kernel)
 B200_NOINL fp2 fp2_mul_c(fp2 a, fp2 b) {
   fpw3 w = fp_mul_wide_triple(a.c0, b.c0, a.c1, b.c1, fp_add_nr(a.c0, a.c1), fp_add_nr(b.c0, b.c1));
   fp_pair r = fp_redc_wide_dual(fpw_sub(w.w2, fpw_add(w.w0, w.w1)), fpw_sub_mod(w.w0, w.w1));
   return fp2{r.r1, r.r0};
-}
-B200_NOINL fp2 fp2_sqr_c(fp2 a) {
-  fp s = fp_add(a.c0, a.c1), d = fp_sub(a.c0, a.c1), t = fp_dbl(a.c0);
-  fp_pair p = fp_mul_dual(s, d, t, a.c1);
-  return fp2{p.r0, p.r1};
-}
-#elif defined(B200_FP2_KTRIPLE)
-// EXPERIMENTAL (pairing_v6.cu): all three Karatsuba products in one row-alternating routine (fp_mul_triple, inlined
-// into the called Fp2 multiply: operands arrive in registers anyway); the squaring uses the dual routine.
-B200_NOINL fp2 fp2_mul_c(fp2 a, fp2 b) {
-  fp_triple t = fp_mul_triple(a.c0, b.c0, a.c1, b.c1, fp_add(a.c0, a.c1), fp_add(b.c0, b.c1));
-  return fp2{fp_sub(t.r0, t.r1), fp_sub(fp_sub(t.r2, t.r0), t.r1)};
 }
 B200_NOINL fp2 fp2_sqr_c(fp2 a) {
   fp s = fp_add(a.c0, a.c1), d = fp_sub(a.c0, a.c1), t = fp_dbl(a.c0);

@@ -72,8 +72,8 @@ int b200_ctx_get_timing(b200_ctx *ctx, char *names, size_t names_len, float *ms,
 /* tuning knobs by name: "msm_window" (0 = auto, else 2..24), "g1_glv" (0 off, 1 on, 2 auto = on for window-sharded calls), "msm_affine_levels" (-1 auto, 0..3 batched-affine
  * tree levels before the bucket kernel; default 0), "g1_prefetch" (0|1), "g2_acc_blocks" (G2 bucket kernel variant: 2 registers,
  * 3 shared-memory accumulator built for 3 blocks/SM, 4 shared-memory accumulator at 2 blocks/SM = default), "pairing_chunks" (1..64 independent chunks of a
- * pairing batch in flight), "pairing_variant" (4 = default kernels; 5 / 6 = experimental dual- / triple-stream Fp2 multiply for the
- * Miller loop / final exponentiation kernels, same results).  Unknown key or bad value -> B200_EINVAL. */
+ * pairing batch in flight), "pairing_variant" (7 = six lanes per pairing, default; 4 = one thread per pairing), "coop_warps" (1..16 warps per block of the
+ * six-lane pairing kernels).  Unknown key or bad value -> B200_EINVAL. */
 int b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int value);
 /* MSM tuning: window bits c (0 = automatic from n); returns previous value */
 int b200_ctx_set_msm_window(b200_ctx *ctx, int c);

@@ -21,8 +21,7 @@ def build(variant="default"):
     """variant: 'default' (lazy-reduction Fp2: capi_basic/capi_msm/capi_serial), 'kcall' (pairing units) or 'kdual'
     (the experimental dual-stream Fp2 of pairing_v5.cu)"""
     so = os.path.join(_DIR, "libemul_%s.so" % variant)
-    flags = {"kcall": ["-DB200_FP2_KCALL"], "kdual": ["-DB200_FP2_KDUAL"], "ktriple": ["-DB200_FP2_KTRIPLE"],
-             "lazy3": ["-DB200_FP2_LAZY3"]}.get(variant, [])
+    flags = {"kcall": ["-DB200_FP2_KCALL"], "lazy3": ["-DB200_FP2_LAZY3"]}.get(variant, [])
     if os.path.exists(os.path.join(_CSRC, "fr.cuh")):
         flags.append("-DEMUL_WITH_FR")
     stamp = so + ".stamp"
@@ -49,7 +48,7 @@ def build_cabi():
     common = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-pthread", "-Wno-unknown-pragmas", "-Wno-unused-variable",
               "-DEMUL_LAUNCH_COOPERATIVE", "-I", os.path.join(_DIR, "mock"), "-I", _DIR,
               "-I", _CSRC, "-I", os.path.join(_ROOT, "include"), "-include", os.path.join(_DIR, "cuda_host_shim.h")]
-    units = ["capi_basic.cu", "capi_msm.cu", "capi_msm_lazy3.cu", "capi_pairing.cu", "pairing_v4.cu", "pairing_v5.cu", "pairing_v6.cu", "capi_serial.cu",
+    units = ["capi_basic.cu", "capi_msm.cu", "capi_pairing.cu", "pairing_v4.cu", "pairing_coop.cu", "capi_serial.cu",
              "capi_fr.cu", "capi_h2c.cu", "capi_gt.cu"]
     from concurrent.futures import ThreadPoolExecutor
 

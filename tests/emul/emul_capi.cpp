@@ -68,7 +68,7 @@ int emul_tower_op(int level, int op, const uint64_t *a, const uint64_t *b, uint6
         case 102: r = fp_sqr(x); break;
         case 103: r = fp_add_nr(x, y); break;  // caller keeps x + y < 2^384
         case 104: r = fp_mul_dual(x, y, y, x).r0; break;          // dual-stream product, first result
-        case 105: r = fp_mul2_c(y, y, x, y).r1; break;            // ... second result of (y*y, x*y)
+        case 105: r = fp_mul_dual(y, y, x, y).r1; break;          // ... second result of (y*y, x*y)
         default: return -1;
       }
       fp_store(po, r);

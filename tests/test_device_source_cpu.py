@@ -37,7 +37,7 @@ class Emul:
         f(*[_p(a) if isinstance(a, np.ndarray) or a is None else a for a in arrs], *extra)
 
 
-@pytest.fixture(scope="module", params=["default", "kcall", "kdual", "ktriple", "lazy3"])
+@pytest.fixture(scope="module", params=["default", "kcall", "lazy3"])
 def em(request):
     return Emul(request.param)
 

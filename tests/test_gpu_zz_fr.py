@@ -1,18 +1,14 @@
 """GPU parity tests (-m gpu) for the scalar-field row: b200_fr_op / to_bytes / from_bytes /
 b200_fr_ntt through the C ABI against the oracle, bit-exact, plus size-independent properties at large n.
 
-STATUS: this row was written after round 1's GPU minutes were spent.  The kernels and the launch plan are validated
-on the CPU harness (tests/test_device_fr_cpu.py: same device source, bit-exact PTX carry models) and compile for sm_100a
-without spills, but have NOT run on hardware yet — hence the non-strict xfail below: the already-validated rows keep
-their green gate whatever happens here, and an XPASS is the first hardware confirmation.  Remove the marker then."""
+STATUS: hardware-validated (round 2, first GPU call: all tests passed on a B200); the same device source is also
+covered on the CPU harness (tests/test_device_fr_cpu.py)."""
 import numpy as np
 import pytest
 
 from tests.test_oracle_fr import Q, to_mont, raw, L
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900),
-              pytest.mark.xfail(strict=False, reason="first hardware run pending (round-1 GPU budget exhausted); "
-                                                     "validated on the CPU harness")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
 
 
 @pytest.fixture(scope="module")

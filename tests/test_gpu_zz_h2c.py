@@ -1,18 +1,15 @@
 """GPU parity tests (-m gpu) for batched hash to curve through the C ABI: the RFC 9380 vectors the
 reference's integration tests hold, and the oracle on seeded inputs — limb-exact on the projective coordinates.
 
-STATUS: like tests/test_gpu_zz_fr.py this row was written after round 1's GPU minutes were spent; the device source is
-validated on the CPU harness (tests/test_device_h2c_cpu.py) and compiles for sm_100a, but has not run on hardware yet.
-Non-strict xfail until the first GPU run; remove the marker when it XPASSes."""
+STATUS: hardware-validated (round 2, first GPU call); the device source is also covered on the CPU harness
+(tests/test_device_h2c_cpu.py)."""
 import numpy as np
 import pytest
 
 from tests import util
 from tests.test_oracle_h2c import VEC, xmd_py, _L
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900),
-              pytest.mark.xfail(strict=False, reason="first hardware run pending (round-1 GPU budget exhausted); "
-                                                     "validated on the CPU harness")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
 
 
 @pytest.fixture(scope="module")

@@ -1,13 +1,12 @@
 """GPU test (-m gpu) of bls12_381_b200.sharding.ShardedPairingProduct on one rank (the multi-rank exchange is covered by
 the gloo tests in tests/test_sharding_cpu.py; the device entry points it composes are validated in
-tests/test_gpu_parity.py).  Written after round 1's GPU minutes were spent: non-strict xfail until its first run."""
+tests/test_gpu_parity.py).  Hardware-validated in round 2."""
 import numpy as np
 import pytest
 
 from tests import util
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900),
-              pytest.mark.xfail(strict=False, reason="first hardware run pending (round-1 GPU budget exhausted)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
 
 
 def test_pairing_product_one_rank(orc):

@@ -62,7 +62,6 @@ def test_device_source_gt_mul_on_cpu(orc, variant):
 
 @pytest.mark.gpu
 @pytest.mark.timeout(900)
-@pytest.mark.xfail(strict=False, reason="first hardware run pending (round-1 GPU budget exhausted); validated on the CPU harness")
 def test_gpu_zz_gt_mul(orc):
     import bls12_381_b200
     eng = bls12_381_b200.Engine()

@@ -1,6 +1,6 @@
 """The MSM unit (capi_msm.cu: digit extraction, counting sort, bucket scheduling, bucket accumulation with its prefetch
 pipeline, giant-bucket split, bucket reduction, warp-cooperative Horner, GLV, batched-affine levels, window sharding) and
-its experimental second build (capi_msm_lazy3.cu) on the CPU: compiled with g++ against the mock CUDA runtime, every
+its Fp2 multiply (row-alternated lazy reduction, B200_FP2_LAZY3) on the CPU: compiled with g++ against the mock CUDA runtime, every
 kernel on the fiber scheduler (match.any, shuffles, atomics, shared memory, barriers), driven through the real C ABI and
 the real Engine class — against the oracle.  Sizes are tiny (one emulated MSM costs ~2 s, mostly the 256-doubling Horner
 chain on the fiber scheduler); the hardware-validated tests at real sizes are tests/test_gpu_parity.py and
@@ -112,16 +112,3 @@ def test_window_sharding_and_sum(eng, orc, data):
     assert eng.lib.b200_g1_sum_dev(eng.h, parts.ctypes.data, 2, out.ctypes.data) == 0
     want = orc.G1.msm_naive(xy[:n], inf[:n], s[:n], threads=4)
     assert np.array_equal(orc.G1.to_affine(out)[0], orc.G1.to_affine(want)[0])
-
-
-def test_experimental_lazy3_build_agrees(eng, orc, data):
-    """capi_msm_lazy3.cu (row-alternated lazy Fp2 multiply) through its own entry point"""
-    xy, inf, s = data[2]
-    case = _edge_set(orc, 2, xy, inf, s, 24)
-    f = eng.lib.b200x_lazy3_g2_msm
-    f.argtypes = [C.c_void_p] * 4 + [C.c_size_t, C.c_void_p]
-    f.restype = C.c_int
-    out = np.empty((1, 36), np.uint64)
-    assert f(eng.h, case[0].ctypes.data, case[1].ctypes.data, case[2].ctypes.data, 24, out.ctypes.data) == 0
-    want = orc.G2.msm_naive(*case, threads=4)
-    assert np.array_equal(orc.G2.to_affine(out)[0], orc.G2.to_affine(want)[0])
