@@ -14,15 +14,18 @@ use bls12_381::{G1Affine, G1Projective, G2Affine, G2Projective, Scalar};
 use bls12381_b200_sys as sys;
 use core::ffi::c_int;
 
+pub mod pairings;
+pub use pairings::{B200Gt, B200MillerLoopResult, Bls12B200};
+
 #[derive(Debug, Clone, Copy, PartialEq, Eq)]
 pub struct Error(pub c_int);
 
-fn check(rc: c_int) -> Result<(), Error> {
+pub(crate) fn check(rc: c_int) -> Result<(), Error> {
     if rc == sys::B200_OK { Ok(()) } else { Err(Error(rc)) }
 }
 
 /// One engine = one GPU (`b200_ctx`): stream + scratch memory.  Calls are serialised inside the library.
-pub struct Engine(*mut sys::b200_ctx);
+pub struct Engine(pub(crate) *mut sys::b200_ctx);
 unsafe impl Send for Engine {}
 unsafe impl Sync for Engine {}
 

@@ -13,6 +13,7 @@ _vp, _sz, _i = C.c_void_p, C.c_size_t, C.c_int
 # name -> argtypes (restype is int unless listed in _RESTYPE)
 SIGNATURES = {
     "b200_ctx_create": [_i, C.POINTER(_vp)],
+    "b200_ctx_create_on_stream": [_i, _vp, C.POINTER(_vp)],
     "b200_ctx_destroy": [_vp],
     "b200_strerror": [_i],
     "b200_last_error": [_vp],
@@ -44,6 +45,9 @@ SIGNATURES = {
     "b200_final_exponentiation_batch": [_vp, _vp, _sz, _vp],
     "b200_pairing_batch": [_vp, _vp, _vp, _vp, _vp, _sz, _vp],
     "b200_multi_miller_loop": [_vp, _vp, _vp, _vp, _vp, _sz, _vp],
+    "b200_multi_miller_loop_dev": [_vp, _vp, _vp, _vp, _vp, _sz, _vp],
+    "b200_pairing_product_batch": [_vp, _vp, _vp, _vp, _vp, _sz, _sz, _i, _vp],
+    "b200_pairing_product_batch_dev": [_vp, _vp, _vp, _vp, _vp, _sz, _sz, _i, _vp],
     "b200_miller_loop_batch_dev": [_vp, _vp, _vp, _vp, _vp, _sz, _vp],
     "b200_final_exponentiation_batch_dev": [_vp, _vp, _sz, _vp],
     "b200_pairing_batch_dev": [_vp, _vp, _vp, _vp, _vp, _sz, _vp],
@@ -52,6 +56,18 @@ SIGNATURES = {
     "b200_multi_miller_loop_prepared": [_vp, _vp, _vp, _vp, _vp, _sz, _vp],
     "b200_g2_prepare_dev": [_vp, _vp, _vp, _sz, _vp],
     "b200_miller_loop_prepared_batch_dev": [_vp, _vp, _vp, _vp, _vp, _sz, _vp],
+    "b200_comm_unique_id": [_vp],
+    "b200_ctx_comm_init": [_vp, _vp, _i, _i],
+    "b200_ctx_comm_destroy": [_vp],
+    "b200_ctx_comm_rank": [_vp],
+    "b200_ctx_comm_world": [_vp],
+    "b200_multi_create": [_i, C.POINTER(_vp)],
+    "b200_multi_destroy": [_vp],
+    "b200_multi_gpus": [_vp],
+    "b200_multi_ctx": [_vp, _i],
+    "b200_multi_set_sharding": [_vp, _i],
+    "b200_multi_g1_msm": [_vp, _vp, _vp, _vp, _sz, _vp],
+    "b200_multi_g2_msm": [_vp, _vp, _vp, _vp, _sz, _vp],
 }
 for _g in ("g1", "g2"):
     SIGNATURES.update({
@@ -66,11 +82,12 @@ for _g in ("g1", "g2"):
         "b200_%s_msm_dev" % _g: [_vp, _vp, _vp, _vp, _sz, _vp],
         "b200_%s_msm_shard_dev" % _g: [_vp, _vp, _vp, _vp, _sz, _i, _i, _vp],
         "b200_%s_sum_dev" % _g: [_vp, _vp, _sz, _vp],
+        "b200_%s_msm_sharded_dev" % _g: [_vp, _vp, _vp, _vp, _sz, _i, _vp],
         "b200_%s_check" % _g: [_vp, _vp, _vp, _sz, _vp],
         "b200_%s_serialize" % _g: [_vp, _vp, _vp, _sz, _i, _vp],
         "b200_%s_deserialize" % _g: [_vp, _vp, _sz, _i, _vp, _vp, _vp],
     })
-_RESTYPE = {"b200_ctx_destroy": None, "b200_strerror": C.c_char_p, "b200_last_error": C.c_char_p,
+_RESTYPE = {"b200_ctx_destroy": None, "b200_multi_destroy": None, "b200_multi_ctx": _vp, "b200_strerror": C.c_char_p, "b200_last_error": C.c_char_p,
             "b200_ctx_stream": _vp, "b200_ctx_launch_count": C.c_uint64}
 
 _lib = None
@@ -81,9 +98,8 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(SO_PATH):
-        from . import build as _build
-        _build.build()
+    from . import build as _build
+    _build.build()          # no-op when the digest stamp of csrc/ + include/ matches the built library (never run a stale .so)
     lib = C.CDLL(SO_PATH)
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the ABI lost a symbol

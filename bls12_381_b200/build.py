@@ -17,7 +17,7 @@ OUT = os.path.join(HERE, "libbls12381_b200.so")
 OBJ = os.path.join(HERE, "build")
 # (source, extra nvcc flags).  The pairing kernels have their own unit with their own Fp2-multiply variant (fp2.cuh).
 UNITS = [("capi_basic.cu", []), ("capi_pairing.cu", []), ("capi_msm.cu", []), ("capi_serial.cu", []),
-         ("pairing_v4.cu", []), ("pairing_coop.cu", []), ("capi_fr.cu", []), ("capi_h2c.cu", []), ("capi_gt.cu", [])]
+         ("pairing_v4.cu", []), ("pairing_coop.cu", []), ("capi_multi.cu", []), ("capi_fr.cu", []), ("capi_h2c.cu", []), ("capi_gt.cu", [])]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
@@ -60,7 +60,7 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(len(UNITS)) as ex:
         objs = list(ex.map(one, UNITS))
-    cmd = [nvcc, "-shared", "-o", OUT] + objs + ["-lcudart"]
+    cmd = [nvcc, "-shared", "-o", OUT] + objs + ["-lcudart", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stderr[-4000:])

@@ -286,9 +286,15 @@ struct stager {
   if (!guard__.ok) return B200_ENODEV
 
 // ================================================================ context
+// enqueue-only combine for capi_multi.cu (no lock, no synchronisation)
+int b200i_sum_enqueue(b200_ctx *ctx, int k, const void *parts, size_t n, void *out) {
+  return k == 1 ? sum_dev<fp>(ctx, parts, n, out) : sum_dev<fp2>(ctx, parts, n, out);
+}
+
 extern "C" {
 
-int b200_ctx_create(int device, b200_ctx **out) {
+int b200_ctx_create(int device, b200_ctx **out) { return b200_ctx_create_on_stream(device, nullptr, out); }
+int b200_ctx_create_on_stream(int device, void *stream, b200_ctx **out) {
   if (out == nullptr) return B200_EINVAL;
   *out = nullptr;
   int count = 0;
@@ -300,8 +306,10 @@ int b200_ctx_create(int device, b200_ctx **out) {
   b200_ctx *c = new (std::nothrow) b200_ctx();
   if (!c) return B200_ENOMEM;
   c->device = device;
+  c->own_stream = stream == nullptr;
+  if (!c->own_stream) c->stream = (cudaStream_t)stream;
   bool ok = cudaSetDevice(device) == cudaSuccess &&
-            cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            (!c->own_stream || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess) &&
             cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking) == cudaSuccess;
   for (int i = 0; ok && i < b200_ctx::N_SYNC_EVENTS; i++) ok = cudaEventCreateWithFlags(&c->ev_sync[i], cudaEventDisableTiming) == cudaSuccess;
@@ -329,12 +337,13 @@ int b200_ctx_create(int device, b200_ctx **out) {
 }
 void b200_ctx_destroy(b200_ctx *ctx) {
   if (!ctx) return;
+  if (ctx->nccl_comm || ctx->comm_buf) b200_ctx_comm_destroy(ctx);
   int prev = 0;
   cudaGetDevice(&prev);
   cudaSetDevice(ctx->device);
   if (ctx->stream) {
     cudaStreamSynchronize(ctx->stream);
-    cudaStreamDestroy(ctx->stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);  // a caller's stream (b200_ctx_create_on_stream) stays the caller's
   }
   if (ctx->stream2) {
     cudaStreamSynchronize(ctx->stream2);
@@ -361,19 +370,24 @@ const char *b200_strerror(int code) {
     case B200_ENODEV: return "no usable CUDA device";
     case B200_ECUDA: return "CUDA runtime error";
     case B200_ENOMEM: return "out of memory";
+    case B200_ENCCL: return "NCCL unavailable or failed";
     default: return "unknown error";
   }
 }
 const char *b200_last_error(const b200_ctx *ctx) { return ctx ? ctx->err : ""; }
 int b200_ctx_device(const b200_ctx *ctx) { return ctx ? ctx->device : -1; }
 void *b200_ctx_stream(const b200_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
-uint64_t b200_ctx_launch_count(const b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+uint64_t b200_ctx_launch_count(const b200_ctx *ctx) {
+  if (!ctx) return 0;
+  std::lock_guard<std::mutex> g(const_cast<b200_ctx *>(ctx)->mu);
+  return ctx->launches;
+}
 int b200_ctx_set_msm_window(b200_ctx *ctx, int c) {
   if (!ctx) return B200_EINVAL;
   if (c != 0 && (c < 2 || c > 24)) return B200_EINVAL;
-  int prev = ctx->msm_c;
+  std::lock_guard<std::mutex> g(ctx->mu);   // serialised with running calls, like b200_ctx_set_tuning
   ctx->msm_c = c;
-  return prev;
+  return B200_OK;
 }
 
 int b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int value) {
@@ -394,10 +408,12 @@ int b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int value) {
   } else if (!strcmp(key, "g1_prefetch")) {
     ctx->tune_g1_prefetch = value != 0;
   } else if (!strcmp(key, "pairing_variant")) {
-    if (value != 4 && value != 7) return B200_EINVAL;  // 4 = one thread per pairing (pairing_v4.cu), 7 = six lanes per pairing
+    if (value != 0 && value != 4 && value != 7) return B200_EINVAL;  // 0 = by batch size, 4 = one thread per pairing, 7 = six lanes
     ctx->tune_pairing_variant = value;
+  } else if (!strcmp(key, "coop_split")) {
+    ctx->tune_coop_split = value != 0;
   } else if (!strcmp(key, "coop_warps")) {
-    if (value < 1 || value > 16) return B200_EINVAL;
+    if (value < 1 || value > 12) return B200_EINVAL;
     ctx->tune_coop_warps = value;
   } else if (!strcmp(key, "pairing_chunks")) {
     if (value < 1 || value > 64) return B200_EINVAL;

@@ -643,6 +643,17 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
       lv_buf[l] = arena_take<char>(ctx, (size_t)maxg * lv_cap[l] * ABY);
     }
   }
+  // whatever path leaves this function (including the error returns below), the main stream is re-joined with both side
+  // streams, so the next call — ordered only against ctx->stream — can never overlap kernels still using the arena
+  struct join_guard {
+    b200_ctx *c;
+    ~join_guard() {
+      cudaEventRecord(c->ev_sync[b200_ctx::N_SYNC_EVENTS - 2], c->stream2);
+      cudaStreamWaitEvent(c->stream, c->ev_sync[b200_ctx::N_SYNC_EVENTS - 2], 0);
+      cudaEventRecord(c->ev_sync[b200_ctx::N_SYNC_EVENTS - 1], c->stream3);
+      cudaStreamWaitEvent(c->stream, c->ev_sync[b200_ctx::N_SYNC_EVENTS - 1], 0);
+    }
+  } join_on_exit{ctx};
   // order the side streams after whatever is still queued on the main stream (previous calls)
   B200_CUDA(ctx, cudaEventRecord(ctx->ev_sync[0], ctx->stream));
   B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_sync[0], 0));
@@ -748,8 +759,8 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
     prev_w = pl.win[j_lo];
     j_top = j_lo - 1;
   }
-  B200_CUDA(ctx, cudaEventRecord(ctx->ev_sync[b200_ctx::N_SYNC_EVENTS - 1], ctx->stream3));
-  B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_sync[b200_ctx::N_SYNC_EVENTS - 1], 0));
+  B200_CUDA(ctx, cudaEventRecord(ctx->ev_sync[b200_ctx::N_SYNC_EVENTS - 3], ctx->stream3));
+  B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_sync[b200_ctx::N_SYNC_EVENTS - 3], 0));
   B200_CUDA(ctx, cudaMemcpyAsync(out, hacc, PB, cudaMemcpyDeviceToDevice, ctx->stream));
   return B200_OK;
 }
@@ -774,6 +785,13 @@ int msm_host(b200_ctx *ctx, const void *points, const uint8_t *inf, const void *
 }
 
 }  // namespace
+
+// enqueue-only MSM (shard of the windows) for capi_multi.cu (no lock, no synchronisation)
+int b200i_msm_enqueue(b200_ctx *ctx, int k, const void *points, const void *inf, const void *scalars, size_t n, int shard,
+                      int n_shards, void *out) {
+  return k == 1 ? msm_dev<fp>(ctx, points, inf, scalars, n, shard, n_shards, out)
+                : msm_dev<fp2>(ctx, points, inf, scalars, n, shard, n_shards, out);
+}
 
 #define CHECK_CTX(ctx)                      \
   if ((ctx) == nullptr) return B200_EINVAL; \

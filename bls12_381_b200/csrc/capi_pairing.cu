@@ -17,6 +17,9 @@ DECL_VARIANT(v4)
 // pairing_coop.cu: flags 1 = Miller loop over prepared coefficients, 2 = final exponentiation (of `in` when bit 0 is clear)
 int b200_pair_coop_launch(b200_ctx *, cudaStream_t, int flags, const void *p, const void *pi, const void *coeffs,
                           const void *qi, const void *in, size_t n, void *out);
+int b200_pair_coop_product_launch(b200_ctx *, cudaStream_t, int final_exp, const void *p, const void *pi, const void *coeffs,
+                                  const void *qi, int terms, size_t n_terms, size_t n_items, void *out);
+int b200_pair_coop_fold_launch(b200_ctx *, cudaStream_t, const void *in, size_t n, void *scratch, void *out);
 
 namespace {
 
@@ -33,15 +36,19 @@ int coop_from_affine(b200_ctx *ctx, cudaStream_t st, const void *p, const void *
   char *co = arena_take<char>(ctx, (size_t)19584 * n);
   rc = b200_pair_g2_prepare_v4(ctx, st, q, qi, n, co);
   if (rc != B200_OK) return rc;
+  if (with_final_exp && ctx->tune_coop_split) {
+    rc = b200_pair_coop_launch(ctx, st, 1, p, pi, co, qi, nullptr, n, out);
+    return rc != B200_OK ? rc : b200_pair_coop_launch(ctx, st, 2, nullptr, nullptr, nullptr, nullptr, out, n, out);
+  }
   return b200_pair_coop_launch(ctx, st, with_final_exp ? 3 : 1, p, pi, co, qi, nullptr, n, out);
 }
 int miller_on(b200_ctx *ctx, cudaStream_t st, const void *p, const void *pi, const void *q, const void *qi, size_t n,
               void *out) {
-  if (ctx->tune_pairing_variant == 7) return coop_from_affine(ctx, st, p, pi, q, qi, n, out, false);
+  if (ctx->coop_for(n)) return coop_from_affine(ctx, st, p, pi, q, qi, n, out, false);
   return b200_pair_miller_v4(ctx, st, p, pi, q, qi, n, out);
 }
 int final_exp_on(b200_ctx *ctx, cudaStream_t st, const void *in, size_t n, void *out) {
-  if (ctx->tune_pairing_variant == 7) return b200_pair_coop_launch(ctx, st, 2, nullptr, nullptr, nullptr, nullptr, in, n, out);
+  if (ctx->coop_for(n)) return b200_pair_coop_launch(ctx, st, 2, nullptr, nullptr, nullptr, nullptr, in, n, out);
   return b200_pair_final_exp_v4(ctx, st, in, n, out);
 }
 int miller_dev(b200_ctx *ctx, const void *p, const void *pi, const void *q, const void *qi, size_t n, void *out) {
@@ -54,7 +61,7 @@ int final_exp_dev(b200_ctx *ctx, const void *in, size_t n, void *out) { return f
 // whole extra wave for the last, partially filled one (2^16 pairs = 1.73 waves of 148 SMs x 4 x 64 threads);
 // with independent chunks in flight the block scheduler back-fills the tail of one kernel with blocks of another.
 int pairing_dev(b200_ctx *ctx, const void *p, const void *pi, const void *q, const void *qi, size_t n, void *out) {
-  if (ctx->tune_pairing_variant == 7) return coop_from_affine(ctx, ctx->stream, p, pi, q, qi, n, out, true);
+  if (ctx->coop_for(n)) return coop_from_affine(ctx, ctx->stream, p, pi, q, qi, n, out, true);
   int chunks = ctx->tune_pairing_chunks;
   if (chunks < 1) chunks = 1;
   // chunking only pays when the batch exceeds one wave of resident threads (148 SMs x 4 blocks x 64 = 37 888): below
@@ -66,6 +73,13 @@ int pairing_dev(b200_ctx *ctx, const void *p, const void *pi, const void *q, con
   }
   B200_CUDA(ctx, cudaEventRecord(ctx->ev_sync[0], ctx->stream));
   B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_sync[0], 0));
+  struct join_guard {   // every exit path (error returns included) re-joins the main stream with the side stream
+    b200_ctx *c;
+    ~join_guard() {
+      cudaEventRecord(c->ev_sync[1], c->stream2);
+      cudaStreamWaitEvent(c->stream, c->ev_sync[1], 0);
+    }
+  } join_on_exit{ctx};
   size_t per = ((n + chunks - 1) / chunks + 63) & ~(size_t)63;
   for (int c = 0; c < chunks; c++) {
     size_t lo = (size_t)c * per, cnt = lo >= n ? 0 : (n - lo < per ? n - lo : per);
@@ -78,11 +92,56 @@ int pairing_dev(b200_ctx *ctx, const void *p, const void *pi, const void *q, con
     if (rc == B200_OK) rc = final_exp_on(ctx, st, co, cnt, co);
     if (rc != B200_OK) return rc;
   }
-  B200_CUDA(ctx, cudaEventRecord(ctx->ev_sync[1], ctx->stream2));
-  B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_sync[1], 0));
   return B200_OK;
 }
-int product_dev(b200_ctx *ctx, const void *in, size_t n, void *out) { return b200_pair_product_v4(ctx, in, n, out); }
+int product_dev(b200_ctx *ctx, const void *in, size_t n, void *out) {
+  if (ctx->coop_products()) {     // multi-block fold, 16 values per group and level
+    int rc = arena_reserve(ctx, 2 * 576 * (n / 16 + 4) + 256);
+    if (rc != B200_OK) return rc;
+    char *scratch = arena_take<char>(ctx, 2 * 576 * (n / 16 + 4));
+    return b200_pair_coop_fold_launch(ctx, ctx->stream, in, n, scratch, out);
+  }
+  return b200_pair_product_v4(ctx, in, n, out);
+}
+// Products of pairings with ONE squaring of the accumulator per bit for all terms of a product (src/pairings.rs:554-603).
+// n_products items of `terms` consecutive pairs each; out[i] = MillerLoopResult (final_exp = 0) or Gt (final_exp = 1).
+int pairing_products_dev(b200_ctx *ctx, const void *p, const void *pi, const void *q, const void *qi, size_t terms,
+                         size_t n_products, int final_exp, void *out) {
+  size_t n = terms * n_products;
+  if (n == 0) return B200_OK;
+  int rc = arena_reserve(ctx, (size_t)19584 * n + 256);
+  if (rc != B200_OK) return rc;
+  char *co = arena_take<char>(ctx, (size_t)19584 * n);
+  rc = b200_pair_g2_prepare_v4(ctx, ctx->stream, q, qi, n, co);
+  if (rc != B200_OK) return rc;
+  return b200_pair_coop_product_launch(ctx, ctx->stream, final_exp, p, pi, co, qi, (int)terms, n, n_products, out);
+}
+// multi_miller_loop over n terms -> ONE value: the terms are cut into chunks of T (shared squaring inside a chunk, one group
+// of six lanes per chunk; T grows with n so that one wave of groups covers the batch), the chunk values are folded by
+// k_coop_product.  `coeffs` = prepared coefficients on the device, or nullptr (then q/qi are affine points to prepare).
+int multi_miller_dev(b200_ctx *ctx, const void *p, const void *pi, const void *q, const void *qi, const void *coeffs, size_t n,
+                     void *out) {
+  size_t capacity = (size_t)ctx->sm_count * (ctx->tune_coop_warps < 1 ? 1 : ctx->tune_coop_warps) * 5;
+  size_t T = (n + capacity - 1) / capacity;
+  if (T < 1) T = 1;
+  if (T > 64) T = 64;
+  size_t items = n == 0 ? 0 : (n + T - 1) / T;
+  size_t need = (coeffs ? 0 : (size_t)19584 * n) + 576 * (items + 1) + 2 * 576 * (items / 16 + 4) + 1024;
+  int rc = arena_reserve(ctx, need);
+  if (rc != B200_OK) return rc;
+  const char *co = (const char *)coeffs;
+  if (!co && n) {
+    char *c2 = arena_take<char>(ctx, (size_t)19584 * n);
+    rc = b200_pair_g2_prepare_v4(ctx, ctx->stream, q, qi, n, c2);
+    if (rc != B200_OK) return rc;
+    co = c2;
+  }
+  char *partial = arena_take<char>(ctx, 576 * (items + 1));
+  char *scratch = arena_take<char>(ctx, 2 * 576 * (items / 16 + 4));
+  rc = b200_pair_coop_product_launch(ctx, ctx->stream, 0, p, pi, co, qi, (int)T, n, items, partial);
+  if (rc != B200_OK) return rc;
+  return b200_pair_coop_fold_launch(ctx, ctx->stream, partial, items, scratch, out);
+}
 int sync(b200_ctx *ctx) {
   B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return B200_OK;
@@ -155,7 +214,7 @@ int b200_miller_loop_prepared_batch_dev(b200_ctx *ctx, const void *p, const void
                                         const void *q_inf, size_t n, void *out) {
   CHECK_CTX(ctx);
   if (n && (!p || !coeffs || !out)) return B200_EINVAL;
-  int rc = ctx->tune_pairing_variant == 7 ? b200_pair_coop_launch(ctx, ctx->stream, 1, p, p_inf, coeffs, q_inf, nullptr, n, out)
+  int rc = ctx->coop_for(n) ? b200_pair_coop_launch(ctx, ctx->stream, 1, p, p_inf, coeffs, q_inf, nullptr, n, out)
                                           : b200_pair_miller_prepared_v4(ctx, ctx->stream, p, p_inf, coeffs, q_inf, n, out);
   return rc != B200_OK ? rc : sync(ctx);
 }
@@ -189,9 +248,12 @@ int b200_multi_miller_loop_prepared(b200_ctx *ctx, const b200_g1_affine *p, cons
     if (q_inf) B200_CUDA(ctx, cudaMemcpyAsync(dqi, q_inf, n, cudaMemcpyHostToDevice, ctx->stream));
     B200_CUDA(ctx, cudaMemcpyAsync(dc, coeffs, 19584 * n, cudaMemcpyHostToDevice, ctx->stream));
   }
-  rc = ctx->tune_pairing_variant == 7 ? b200_pair_coop_launch(ctx, ctx->stream, 1, dp, dpi, dc, dqi, nullptr, n, dml)
-                                      : b200_pair_miller_prepared_v4(ctx, ctx->stream, dp, dpi, dc, dqi, n, dml);
-  if (rc == B200_OK) rc = product_dev(ctx, dml, n, dout);
+  if (ctx->coop_products()) {
+    rc = multi_miller_dev(ctx, dp, dpi, nullptr, dqi, dc, n, dout);
+  } else {
+    rc = b200_pair_miller_prepared_v4(ctx, ctx->stream, dp, dpi, dc, dqi, n, dml);
+    if (rc == B200_OK) rc = product_dev(ctx, dml, n, dout);
+  }
   if (rc != B200_OK) return rc;
   B200_CUDA(ctx, cudaMemcpyAsync(out, dout, 576, cudaMemcpyDeviceToHost, ctx->stream));
   return sync(ctx);
@@ -244,10 +306,44 @@ int b200_multi_miller_loop(b200_ctx *ctx, const b200_g1_affine *p, const uint8_t
   if (h.rc != B200_OK) return h.rc;
   void *dml = stage_take(ctx, 576 * (n ? n : 1));
   void *dout = stage_take(ctx, 576);
-  int rc = miller_dev(ctx, h.dp, h.dpi, h.dq, h.dqi, n, dml);
-  if (rc == B200_OK) rc = product_dev(ctx, dml, n, dout);
+  int rc;
+  if (ctx->coop_products()) {
+    rc = multi_miller_dev(ctx, h.dp, h.dpi, h.dq, h.dqi, nullptr, n, dout);
+  } else {
+    rc = miller_dev(ctx, h.dp, h.dpi, h.dq, h.dqi, n, dml);
+    if (rc == B200_OK) rc = product_dev(ctx, dml, n, dout);
+  }
   if (rc != B200_OK) return rc;
   B200_CUDA(ctx, cudaMemcpyAsync(out, dout, 576, cudaMemcpyDeviceToHost, ctx->stream));
+  return sync(ctx);
+}
+// ---- products of pairings (Groth16 / BLS batch verification shape): n_products x `terms` pairs -> n_products values
+int b200_pairing_product_batch_dev(b200_ctx *ctx, const void *p, const void *p_inf, const void *q, const void *q_inf,
+                                   size_t terms, size_t n_products, int final_exp, void *out) {
+  CHECK_CTX(ctx);
+  if (terms == 0 || (n_products && (!p || !q || !out))) return B200_EINVAL;
+  int rc = pairing_products_dev(ctx, p, p_inf, q, q_inf, terms, n_products, final_exp, out);
+  return rc != B200_OK ? rc : sync(ctx);
+}
+int b200_multi_miller_loop_dev(b200_ctx *ctx, const void *p, const void *p_inf, const void *q, const void *q_inf, size_t n,
+                               void *out) {
+  CHECK_CTX(ctx);
+  if (!out || (n && (!p || !q))) return B200_EINVAL;
+  int rc = multi_miller_dev(ctx, p, p_inf, q, q_inf, nullptr, n, out);
+  return rc != B200_OK ? rc : sync(ctx);
+}
+int b200_pairing_product_batch(b200_ctx *ctx, const b200_g1_affine *p, const uint8_t *p_inf, const b200_g2_affine *q,
+                               const uint8_t *q_inf, size_t terms, size_t n_products, int final_exp, b200_fp12 *out) {
+  CHECK_CTX(ctx);
+  if (terms == 0 || (n_products && (!p || !q || !out))) return B200_EINVAL;
+  size_t n = terms * n_products;
+  if (n == 0) return B200_OK;
+  host_pairs h(ctx, p, p_inf, q, q_inf, n, 576 * n_products + 512);
+  if (h.rc != B200_OK) return h.rc;
+  void *dout = stage_take(ctx, 576 * n_products);
+  int rc = pairing_products_dev(ctx, h.dp, h.dpi, h.dq, h.dqi, terms, n_products, final_exp, dout);
+  if (rc != B200_OK) return rc;
+  B200_CUDA(ctx, cudaMemcpyAsync(out, dout, 576 * n_products, cudaMemcpyDeviceToHost, ctx->stream));
   return sync(ctx);
 }
 

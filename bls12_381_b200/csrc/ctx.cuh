@@ -12,6 +12,7 @@
 struct b200_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  bool own_stream = true;   // false: the caller's stream (b200_ctx_create_on_stream), never destroyed by the ctx
   // side streams of an MSM: bucket reduction (stream2) and the serial Horner chain (stream3) of one window
   // group overlap the bucket accumulation of the next group on `stream`
   cudaStream_t stream2 = nullptr, stream3 = nullptr;
@@ -55,10 +56,21 @@ struct b200_ctx {
   void (*fr_state_free)(void *) = nullptr;
   // Miller loop / final exponentiation kernels: 4 = pairing_v4.cu, one thread per pairing (round 1).  The dual- / triple-
   // stream Fp2-multiply builds (v5 / v6) measured slower on B200 (63.5 / 67.4 vs 59.3 ms at 2^16 pairs) and were removed.
-  // 7 = pairing_coop.cu: six lanes per pairing, Fp12 distributed over the lanes (round 2; default)
-  int tune_pairing_variant = 7;
+  // 7 = pairing_coop.cu: six lanes per pairing, Fp12 distributed over the lanes (round 2).
+  // 0 = automatic (default): batched pairings / Miller loops / final exponentiations of at most COOP_MAX_PAIRS items use the
+  // six-lane kernels (one wave needs 8 880 pairs instead of 37 888: 9.1 vs 22.0 ms at 8 192 pairs, 16.0 vs 22.7 ms at 16 384),
+  // larger batches the one-thread-per-pairing kernels (59.3 vs 61.8 ms at 65 536); products (shared squaring) always 7.
+  int tune_pairing_variant = 0;
+  static constexpr size_t COOP_MAX_PAIRS = 28672;
+  bool coop_for(size_t n) const { return tune_pairing_variant == 7 || (tune_pairing_variant == 0 && n <= COOP_MAX_PAIRS); }
+  bool coop_products() const { return tune_pairing_variant != 4; }
   int tune_coop_warps = 12;          // warps per block (one block per SM) of the lane-cooperative pairing kernels, 1..16
-  bool coop_attr_done = false;       // cudaFuncSetAttribute(max dynamic shared memory) done on this device
+  int tune_coop_split = 1;           // 1: Miller loop and final exponentiation of a pairing batch as two launches of the kernel
+  bool coop_attr_done[7] = {};       // cudaFuncSetAttribute(max dynamic shared memory) done on this device, per kernel build
+  // multi-GPU (capi_multi.cu): NCCL communicator of this rank, and a (world + 1) x 576-byte exchange buffer on the device
+  void *nccl_comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
+  char *comm_buf = nullptr;       // cudaFuncSetAttribute(max dynamic shared memory) done on this device
 };
 
 namespace b200 {

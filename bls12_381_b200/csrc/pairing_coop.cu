@@ -3,7 +3,7 @@
 // memory.  Replaces, with bit-identical results, src/pairings.rs miller_loop :668-694 + ell :696-707 (over G2Prepared
 // coefficients :498-546), multi_miller_loop :554-603 and final_exponentiation :48-176.
 //
-// Pairs are handed to warps in a grid-stride loop (5 pairs per warp and turn); a block is BLOCK_WARPS warps, one block
+// Pairs are handed to warps in a grid-stride loop (5 pairs per warp and turn; the groups of a warp synchronise independently); a block is `coop_warps` warps, one block
 // per SM.  The G2 line coefficients come from memory (prepared by k_g2_prepare, 68 x 288 B per Q, in the order the loop
 // consumes them); the lanes 0..3 of a group multiply them by P.x / P.y, all six then apply the sparse line to f.
 #define B200_FP2_KCALL 1  // (the few plain Fp2 products in the inversion: Karatsuba over fp_mul_c)
@@ -19,7 +19,7 @@ constexpr int S_C1 = 18, S_C4 = 19;  // board slots of the scaled line coefficie
 
 // f <- f * line(coeffs, P)   (ell, src/pairings.rs:696-707: f.mul_by_014(c.2, c.1 * p.x, c.0 * p.y))
 // co = one coefficient triple (a, b, c) of 3 x 96 bytes; pc = P.x on lanes 0,1 and P.y on lanes 2,3 of the group
-B200_DEV fp2 co_ell(const cgrp &g, const fp2 &f, const char *co, const fp &pc) {
+B200_NOINL fp2 co_ell(cgrp g, fp2 f, const char *co, fp pc) {
   const int k = g.k;
   const int off = k == 0 ? 96 : (k == 1 ? 144 : (k == 3 ? 48 : 0));  // b.c0, b.c1, a.c0, a.c1
   fp m = fp_mul_c(fp_load(co + off), pc);
@@ -42,8 +42,35 @@ B200_DEV fp2 co_miller_prepared(const cgrp &g, const char *coeffs, const fp &pc)
   return co_conj(g, f);  // BLS_X_IS_NEGATIVE
 }
 
+// multi_miller_loop over T prepared terms with ONE squaring of f per bit for all terms (src/pairings.rs:554-603):
+//   f <- f^2 * prod_t line_t   per bit.   Terms with an identity on either side are skipped (:566-569, :578-581).
+// coeffs / pxy / pinf / qinf are indexed by the absolute term number first + t.
+B200_DEV fp2 co_miller_prepared_multi(const cgrp &g, const char *coeffs, const char *pxy, const uint8_t *pinf,
+                                      const uint8_t *qinf, size_t first, int T) {
+  fp2 f = co_one(g);
+  const unsigned long long x = B200_BLS_X >> 1;
+  const int poff = (g.k & 2) ? 48 : 0;
+  int idx = 0;
+#pragma unroll 1
+  for (int b = 61; b >= -1; b--) {       // b = -1: the final doubling step after the loop
+    const bool bit = b >= 0 && ((x >> b) & 1);
+#pragma unroll 1
+    for (int t = 0; t < T; t++) {
+      const size_t i = first + t;
+      if ((pinf != nullptr && pinf[i] != 0) || (qinf != nullptr && qinf[i] != 0)) continue;   // uniform over the group
+      const char *co = coeffs + (size_t)19584 * i + 288 * idx;
+      fp pc = fp_load_ro(pxy + 96 * i + poff);
+      f = co_ell(g, f, co, pc);
+      if (bit) f = co_ell(g, f, co + 288, pc);
+    }
+    idx += bit ? 2 : 1;
+    if (b >= 0) f = co_sqr(g, f);
+  }
+  return co_conj(g, f);
+}
+
 // f^|x| then conjugate (cycolotomic_exp, src/pairings.rs:115-132); the first multiplication (1 * f) is a copy
-B200_DEV fp2 co_cyclotomic_exp(const cgrp &g, const fp2 &f) {
+B200_NOINL fp2 co_cyclotomic_exp(cgrp g, fp2 f) {
   fp2 r = f;
 #pragma unroll 1
   for (int b = 62; b >= 0; b--) {
@@ -83,28 +110,88 @@ B200_DEV fp2 co_final_exponentiation(const cgrp &g, const fp2 &f, const uint32_t
 
 constexpr int CO_FLAG_MILLER = 1, CO_FLAG_FINAL_EXP = 2;
 
+// Product mode: item i = the product over the `terms` consecutive pairs [i * terms, (i + 1) * terms) — ONE Miller value
+// (and, with final_exp, one Gt) per item.  Groth16 / BLS batch verification: terms = 3..4, n_items = number of proofs;
+// a single large product: n_items = number of term chunks, the partial products are multiplied by k_coop_product.
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) k_coop_pairing_product(int final_exp, const char *pxy, const uint8_t *pinf,
+                                                                 const char *coeffs, const uint8_t *qinf, int terms,
+                                                                 size_t n_terms, size_t n_items, char *out,
+                                                                 const uint32_t *pow2) {
+  B200_DYN_SMEM(uint32_t, smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const int grp = lane / CO_LANES;
+  if (grp >= CO_GROUPS) return;   // lanes 30, 31: no group
+  cgrp g;
+  g.k = lane - CO_LANES * grp;
+  g.mask = 0x3fu << (CO_LANES * grp);
+  g.bd = smem + (size_t)(warp * CO_GROUPS + grp) * CO_BOARD;
+  const size_t stride = (size_t)gridDim.x * nwarp * CO_GROUPS;
+#pragma unroll 1
+  for (size_t base = ((size_t)blockIdx.x * nwarp + warp) * CO_GROUPS; base < n_items; base += stride) {
+    const size_t i = base + grp;
+    if (i >= n_items) continue;
+    const bool valid = true;
+    size_t first = i * (size_t)terms;
+    int T = first + terms <= n_terms ? terms : (int)(n_terms - first);   // the last chunk of a large product may be short
+    fp2 f = co_miller_prepared_multi(g, coeffs, pxy, pinf, qinf, first, T);
+    if (final_exp) f = co_final_exponentiation(g, f, pow2);
+    if (valid) co_store12(g, out + 576 * i, f);
+  }
+}
+
+// out[b] = product of in[b * per .. (b + 1) * per) (clipped to n), one item per GROUP; used to fold the partial products of
+// a large multi_miller_loop: launch with n_out = ceil(n / per) groups, repeat until one value is left.
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) k_coop_product(const char *in, size_t n, int per, size_t n_out, char *out) {
+  B200_DYN_SMEM(uint32_t, smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const int grp = lane / CO_LANES;
+  if (grp >= CO_GROUPS) return;   // lanes 30, 31: no group
+  cgrp g;
+  g.k = lane - CO_LANES * grp;
+  g.mask = 0x3fu << (CO_LANES * grp);
+  g.bd = smem + (size_t)(warp * CO_GROUPS + grp) * CO_BOARD;
+  const size_t stride = (size_t)gridDim.x * nwarp * CO_GROUPS;
+#pragma unroll 1
+  for (size_t base = ((size_t)blockIdx.x * nwarp + warp) * CO_GROUPS; base < n_out; base += stride) {
+    const size_t i = base + grp;
+    if (i >= n_out) continue;
+    const bool valid = true;
+    fp2 f = co_one(g);
+#pragma unroll 1
+    for (int t = 0; t < per; t++) {
+      size_t j = i * (size_t)per + t;
+      if (j >= n) break;
+      f = co_mul(g, f, co_load12(g, in + 576 * j));
+    }
+    if (valid) co_store12(g, out + 576 * i, f);
+  }
+}
+
 // flags & 1: f = Miller loop of (P_i, prepared Q_i) else f = in[i];  flags & 2: f = final_exponentiation(f).
 // One warp = 5 pairs; grid-stride over groups of 5.
-__global__ void __launch_bounds__(512, 1) k_coop_pairing(int flags, const char *pxy, const uint8_t *pinf, const char *coeffs,
+template <int MAXT, int FLAGS>
+__global__ void __launch_bounds__(MAXT, 1) k_coop_pairing(int, const char *pxy, const uint8_t *pinf, const char *coeffs,
                                                         const uint8_t *qinf, const char *in, size_t n, char *out,
                                                         const uint32_t *pow2) {
   B200_DYN_SMEM(uint32_t, smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  int grp = lane / CO_LANES;
+  const int grp = lane / CO_LANES;
+  if (grp >= CO_GROUPS) return;   // lanes 30, 31: no group
   cgrp g;
-  g.live = grp < CO_GROUPS;
   g.k = lane - CO_LANES * grp;
-  if (!g.live) grp = 0;
+  g.mask = 0x3fu << (CO_LANES * grp);
   g.bd = smem + (size_t)(warp * CO_GROUPS + grp) * CO_BOARD;
   const size_t stride = (size_t)gridDim.x * nwarp * CO_GROUPS;
 #pragma unroll 1
   for (size_t base = ((size_t)blockIdx.x * nwarp + warp) * CO_GROUPS; base < n; base += stride) {
-    size_t i = base + grp;
-    const bool valid = g.live && i < n;
-    if (i >= n) i = n - 1;
+    const size_t i = base + grp;
+    if (i >= n) continue;   // groups are independent: nothing to do for this one
+    const bool valid = true;
     fp2 f;
     bool ident = false;
-    if (flags & CO_FLAG_MILLER) {
+    if (FLAGS & CO_FLAG_MILLER) {
       ident = (pinf != nullptr && pinf[i] != 0) || (qinf != nullptr && qinf[i] != 0);
       // lanes 0,1 of a group keep P.x, lanes 2,3 P.y (the others never use theirs)
       fp pc = fp_load_ro(pxy + 96 * i + ((g.k & 2) ? 48 : 0));
@@ -113,7 +200,7 @@ __global__ void __launch_bounds__(512, 1) k_coop_pairing(int flags, const char *
     } else {
       f = co_load12(g, in + 576 * i);
     }
-    if (flags & CO_FLAG_FINAL_EXP) f = co_final_exponentiation(g, f, pow2);
+    if (FLAGS & CO_FLAG_FINAL_EXP) f = co_final_exponentiation(g, f, pow2);
     if (valid) co_store12(g, out + 576 * i, f);
   }
 }
@@ -126,19 +213,107 @@ int b200_pair_coop_launch(b200_ctx *ctx, cudaStream_t strm, int flags, const voi
   if (n == 0) return B200_OK;
   int warps = ctx->tune_coop_warps;
   if (warps < 1) warps = 1;
-  if (warps > 16) warps = 16;
+  if (warps > 12) warps = 12;
   size_t turns = (n + CO_GROUPS - 1) / CO_GROUPS;                      // warp-turns of 5 pairs
   unsigned grid = (unsigned)((turns + warps - 1) / warps);
   if (grid > (unsigned)ctx->sm_count) grid = (unsigned)ctx->sm_count;  // one block per SM, grid-stride beyond that
   size_t smem = (size_t)warps * CO_WARP_SMEM;
-#ifndef B200_HOST_EMUL
-  if (!ctx->coop_attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k_coop_pairing, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * CO_WARP_SMEM);
-    if (e != cudaSuccess) return b200::set_err(ctx, e, "cudaFuncSetAttribute(k_coop_pairing)");
-    ctx->coop_attr_done = true;
+  // the kernel is compiled per phase (1 = Miller loop, 2 = final exponentiation, 3 = both in one launch) and per register
+  // budget (255 registers for <= 8 warps per SM, 168 for <= 12): the instruction cache, not the multiplier, limits these
+  // kernels (ncu: no_instruction is the second stall), and a phase-specific kernel keeps every warp of an SM in the same
+  // few functions
+#ifdef B200_HOST_EMUL
+#define CO_SET_ATTR(MAXT, FL)
+#else
+#define CO_SET_ATTR(MAXT, FL)                                                                                                \
+  if (!ctx->coop_attr_done[(MAXT == 256 ? 0 : 3) + FL - 1]) {                                                                \
+    cudaError_t e = cudaFuncSetAttribute(k_coop_pairing<MAXT, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+                                         (MAXT / 32) * CO_WARP_SMEM);                                                        \
+    if (e != cudaSuccess) return b200::set_err(ctx, e, "cudaFuncSetAttribute(k_coop_pairing)");                              \
+    ctx->coop_attr_done[(MAXT == 256 ? 0 : 3) + FL - 1] = true;                                                              \
   }
 #endif
-  B200_LAUNCH_ON(ctx, strm, k_coop_pairing, grid, 32 * warps, smem, flags, (const char *)p, (const uint8_t *)pi,
-                 (const char *)coeffs, (const uint8_t *)qi, (const char *)in, n, (char *)out, (const uint32_t *)ctx->inv_pow2);
+#define CO_LAUNCH(MAXT, FL)                                                                                                  \
+  do {                                                                                                                       \
+    CO_SET_ATTR(MAXT, FL)                                                                                                    \
+    B200_LAUNCH_ON(ctx, strm, (k_coop_pairing<MAXT, FL>), grid, 32 * warps, smem, flags, (const char *)p,                    \
+                   (const uint8_t *)pi, (const char *)coeffs, (const uint8_t *)qi, (const char *)in, n, (char *)out,        \
+                   (const uint32_t *)ctx->inv_pow2);                                                                         \
+  } while (0)
+  if (warps > 12) warps = 12;
+  smem = (size_t)warps * CO_WARP_SMEM;
+  if (warps <= 8) {
+    if (flags == 1) CO_LAUNCH(256, 1); else if (flags == 2) CO_LAUNCH(256, 2); else CO_LAUNCH(256, 3);
+  } else {
+    if (flags == 1) CO_LAUNCH(384, 1); else if (flags == 2) CO_LAUNCH(384, 2); else CO_LAUNCH(384, 3);
+  }
+#undef CO_LAUNCH
+#undef CO_SET_ATTR
   return B200_OK;
+}
+
+namespace {
+// launch geometry shared by the product kernels: `items` groups of work, `warps` warps per block, one block per SM
+inline void coop_geometry(b200_ctx *ctx, size_t items, int *warps, unsigned *grid, size_t *smem) {
+  int w = ctx->tune_coop_warps;
+  if (w < 1) w = 1;
+  if (w > 12) w = 12;
+  size_t turns = (items + CO_GROUPS - 1) / CO_GROUPS;
+  if (turns < (size_t)w) w = turns ? (int)turns : 1;     // small jobs: no empty warps
+  unsigned g = (unsigned)((turns + w - 1) / w);
+  if (g > (unsigned)ctx->sm_count) g = (unsigned)ctx->sm_count;
+  if (g < 1) g = 1;
+  *warps = w;
+  *grid = g;
+  *smem = (size_t)w * CO_WARP_SMEM;
+}
+}  // namespace
+
+// one Miller value (final_exp = 0) or Gt (final_exp = 1) per item = product over `terms` consecutive prepared pairs
+int b200_pair_coop_product_launch(b200_ctx *ctx, cudaStream_t strm, int final_exp, const void *p, const void *pi,
+                                  const void *coeffs, const void *qi, int terms, size_t n_terms, size_t n_items, void *out) {
+  if (n_items == 0) return B200_OK;
+  int warps;
+  unsigned grid;
+  size_t smem;
+  coop_geometry(ctx, n_items, &warps, &grid, &smem);
+#ifndef B200_HOST_EMUL
+  if (!ctx->coop_attr_done[6]) {
+    cudaError_t e = cudaFuncSetAttribute(k_coop_pairing_product<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * CO_WARP_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_coop_product<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * CO_WARP_SMEM);
+    if (e != cudaSuccess) return b200::set_err(ctx, e, "cudaFuncSetAttribute(k_coop_pairing_product)");
+    ctx->coop_attr_done[6] = true;
+  }
+#endif
+  B200_LAUNCH_ON(ctx, strm, k_coop_pairing_product<384>, grid, 32 * warps, smem, final_exp, (const char *)p, (const uint8_t *)pi,
+                 (const char *)coeffs, (const uint8_t *)qi, terms, n_terms, n_items, (char *)out, (const uint32_t *)ctx->inv_pow2);
+  return B200_OK;
+}
+// out[0] = product of in[0..n) (n = 0: one()); `scratch` holds ceil(n / 16) Fp12 values; in is not modified
+int b200_pair_coop_fold_launch(b200_ctx *ctx, cudaStream_t strm, const void *in, size_t n, void *scratch, void *out) {
+  constexpr int PER = 16;
+  const char *src = (const char *)in;
+  char *bufs[2] = {(char *)scratch, (char *)scratch + 576 * ((n + PER - 1) / PER + 1)};
+  int which = 0;
+  for (;;) {
+    size_t n_out = n <= (size_t)PER ? 1 : (n + PER - 1) / PER;
+    char *dst = n_out == 1 ? (char *)out : bufs[which];
+    int warps;
+    unsigned grid;
+    size_t smem;
+    coop_geometry(ctx, n_out, &warps, &grid, &smem);
+#ifndef B200_HOST_EMUL
+    if (!ctx->coop_attr_done[6]) {
+      cudaError_t e = cudaFuncSetAttribute(k_coop_pairing_product<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * CO_WARP_SMEM);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_coop_product<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * CO_WARP_SMEM);
+      if (e != cudaSuccess) return b200::set_err(ctx, e, "cudaFuncSetAttribute(k_coop_product)");
+      ctx->coop_attr_done[6] = true;
+    }
+#endif
+    B200_LAUNCH_ON(ctx, strm, k_coop_product<384>, grid, 32 * warps, smem, src, n, PER, n_out, dst);
+    if (n_out == 1) return B200_OK;
+    src = dst;
+    n = n_out;
+    which ^= 1;
+  }
 }

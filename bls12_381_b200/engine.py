@@ -49,10 +49,15 @@ class Engine:
     AFF = {1: 12, 2: 24}
     PROJ = {1: 18, 2: 36}
 
-    def __init__(self, device=-1):
+    def __init__(self, device=-1, stream=None):
+        """stream: optional cudaStream_t (int) owned by the caller, e.g. torch.cuda.Stream().cuda_stream — the ctx then
+        enqueues on it and never destroys it (b200_ctx_create_on_stream)"""
         self.lib = _lib.load()
         h = C.c_void_p()
-        rc = self.lib.b200_ctx_create(int(device), C.byref(h))
+        if stream:
+            rc = self.lib.b200_ctx_create_on_stream(int(device), C.c_void_p(int(stream)), C.byref(h))
+        else:
+            rc = self.lib.b200_ctx_create(int(device), C.byref(h))
         if rc != 0:
             raise B200Error("b200_ctx_create: %s" % self.lib.b200_strerror(rc).decode())
         self.h = h
@@ -345,6 +350,26 @@ class Engine:
                                                  _hp(out)), "multi_miller_loop")
         return out
 
+    def pairing_product_batch(self, pxy, pinf, qxy, qinf, terms, final_exp=True):
+        """n_products x `terms` pairs -> (n_products, 72): multi_miller_loop of every product with one shared squaring per
+        bit (src/pairings.rs:554-603), followed by final_exponentiation when final_exp"""
+        pxy, pinf, qxy, qinf = self._pairs(pxy, pinf, qxy, qinf)
+        if terms < 1 or pxy.shape[0] % terms:
+            raise ValueError("pairing_product_batch: the number of pairs must be a multiple of terms")
+        npr = pxy.shape[0] // terms
+        out = np.empty((npr, 72), np.uint64)
+        self._ck(self.lib.b200_pairing_product_batch(self.h, _hp(pxy), _hp(pinf), _hp(qxy), _hp(qinf), terms, npr,
+                                                     int(bool(final_exp)), _hp(out)), "pairing_product_batch")
+        return out
+
+    def pairing_product_batch_dev(self, p, pinf, q, qinf, terms, n_products, out, final_exp=True):
+        self._ck(self.lib.b200_pairing_product_batch_dev(self.h, _dp(p), _dp(pinf), _dp(q), _dp(qinf), terms, n_products,
+                                                         int(bool(final_exp)), _dp(out)), "pairing_product_batch_dev")
+
+    def multi_miller_loop_dev(self, p, pinf, q, qinf, n, out):
+        self._ck(self.lib.b200_multi_miller_loop_dev(self.h, _dp(p), _dp(pinf), _dp(q), _dp(qinf), n, _dp(out)),
+                 "multi_miller_loop_dev")
+
     def g2_prepare(self, qxy, qinf=None):
         """G2Prepared::from for a batch -> (n, 68, 36) uint64 line coefficients (src/pairings.rs:504-546)"""
         qxy = _np(qxy, np.uint64, 24)
@@ -384,6 +409,31 @@ class Engine:
         self._ck(getattr(self.lib, self._g(k) + "msm_shard_dev")(self.h, _dp(xy), _dp(inf), _dp(s), n, shard, n_shards,
                                                                  _dp(out)), "msm_dev")
 
+    # ---------------------------------------------------------------- multi-GPU: one process per GPU (capi_multi.cu)
+    SHARD = dict(window=0, points=1)
+
+    def comm_unique_id(self):
+        """128-byte NCCL id made on rank 0; ship it to the other ranks, then comm_init everywhere"""
+        buf = (C.c_uint8 * 128)()
+        self._ck(self.lib.b200_comm_unique_id(buf), "comm_unique_id")
+        return bytes(buf)
+
+    def comm_init(self, uid, rank, world):
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(uid))
+        self._ck(self.lib.b200_ctx_comm_init(self.h, buf, int(rank), int(world)), "comm_init")
+
+    def comm_destroy(self):
+        self._ck(self.lib.b200_ctx_comm_destroy(self.h), "comm_destroy")
+
+    @property
+    def comm_world(self):
+        return int(self.lib.b200_ctx_comm_world(self.h))
+
+    def msm_sharded_dev(self, k, xy, inf, s, n, out, mode="window"):
+        """collective: shard + ncclAllGather + combine inside the library, one host sync at the end"""
+        self._ck(getattr(self.lib, self._g(k) + "msm_sharded_dev")(self.h, _dp(xy), _dp(inf), _dp(s), n, self.SHARD[mode],
+                                                                   _dp(out)), "msm_sharded_dev")
+
     def sum_dev(self, k, parts, n, out):
         self._ck(getattr(self.lib, self._g(k) + "sum_dev")(self.h, _dp(parts), n, _dp(out)), "sum_dev")
 
@@ -400,3 +450,43 @@ class Engine:
 
     def fp12_product_dev(self, f, n, out):
         self._ck(self.lib.b200_fp12_product_dev(self.h, _dp(f), n, _dp(out)), "fp12_product_dev")
+
+
+class MultiEngine:
+    """One process, several GPUs (b200_multi_*): owns a ctx + NCCL communicator + host thread per device."""
+
+    def __init__(self, n_gpus=0, mode="points"):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        rc = self.lib.b200_multi_create(int(n_gpus), C.byref(h))
+        if rc != 0:
+            raise B200Error("b200_multi_create: %s" % self.lib.b200_strerror(rc).decode())
+        self.h = h
+        self.set_sharding(mode)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b200_multi_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    @property
+    def gpus(self):
+        return int(self.lib.b200_multi_gpus(self.h))
+
+    def set_sharding(self, mode):
+        rc = self.lib.b200_multi_set_sharding(self.h, Engine.SHARD[mode])
+        if rc != 0:
+            raise B200Error("b200_multi_set_sharding: %s" % self.lib.b200_strerror(rc).decode())
+
+    def msm(self, k, xy, inf, s):
+        xy, s = _np(xy, np.uint64, Engine.AFF[k]), _np(s, np.uint8, 32)
+        if xy.shape[0] != s.shape[0]:
+            raise ValueError("points/scalars length mismatch")
+        inf = None if inf is None else _np(inf, np.uint8)
+        out = np.empty((1, Engine.PROJ[k]), np.uint64)
+        rc = getattr(self.lib, "b200_multi_g%d_msm" % k)(self.h, _hp(xy), _hp(inf), _hp(s), xy.shape[0], _hp(out))
+        if rc != 0:
+            raise B200Error("b200_multi_g%d_msm: %s" % (k, self.lib.b200_strerror(rc).decode()))
+        return out

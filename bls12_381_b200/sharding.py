@@ -1,5 +1,9 @@
 """Multi-GPU host logic (one process per GPU, torch.distributed).
 
+Since round 2 the product path for MSM is INSIDE the library (csrc/capi_multi.cu: b200_ctx_comm_init +
+b200_g{1,2}_msm_sharded_dev, or the single-process b200_multi_*); this module keeps the same call sequence on top of
+torch.distributed for hosts that bring their own collective, and is what the gloo CPU tests exercise.
+
 MSM shards by scalar window (north_star / SURVEY §8e): every rank holds all points and scalars, computes the
 partial group element  sum_{w = rank mod world} 2^(c*w) * S_w  with `b200_g{1,2}_msm_shard_dev`, the ranks
 exchange their 144-byte (G1) / 288-byte (G2) partials with ONE all_gather, and each rank adds the partials
@@ -47,6 +51,11 @@ class ShardedMSM:
         """out (1, 18k) <- sum_i points[i]*scalars[i] on every rank; parts = (world, 18k) scratch"""
         if self.world == 1:
             self.eng.msm_dev(self.k, xy, inf, scalars, n, out)
+            return out
+        if getattr(self.eng, "comm_world", 1) == self.world:
+            # the library owns the NCCL communicator (b200_ctx_comm_init): shard + ncclAllGather + combine on one stream,
+            # no host synchronisation in between (round 2; the torch.distributed route below stays for hosts without it)
+            self.eng.msm_sharded_dev(self.k, xy, inf, scalars, n, out, mode=self.mode)
             return out
         if self.mode == "window":
             self.eng.msm_dev(self.k, xy, inf, scalars, n, out, shard=self.rank, n_shards=self.world)

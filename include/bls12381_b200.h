@@ -51,11 +51,16 @@ enum {
   B200_EINVAL = -1,  /* NULL pointer / bad size / bad op */
   B200_ENODEV = -2,  /* no usable CUDA device */
   B200_ECUDA = -3,   /* CUDA runtime error (see b200_last_error) */
-  B200_ENOMEM = -4
+  B200_ENOMEM = -4,
+  B200_ENCCL = -5    /* NCCL missing (libnccl.so.2 could not be loaded) or an NCCL call failed */
 };
 
 /* ---- context ------------------------------------------------------------------------------- */
 int b200_ctx_create(int device /* CUDA ordinal, -1 = current */, b200_ctx **out);
+/* same, but the ctx enqueues its work on the CALLER's stream (a cudaStream_t of `device`), which stays owned by the caller
+ * and must outlive the ctx — lets a host runtime (e.g. a PyTorch process) keep one stream for its own copies / events and
+ * the library's kernels.  stream = NULL is b200_ctx_create. */
+int b200_ctx_create_on_stream(int device, void *stream, b200_ctx **out);
 void b200_ctx_destroy(b200_ctx *ctx);
 const char *b200_strerror(int code);
 const char *b200_last_error(const b200_ctx *ctx); /* text of the last CUDA error on this ctx */
@@ -72,10 +77,10 @@ int b200_ctx_get_timing(b200_ctx *ctx, char *names, size_t names_len, float *ms,
 /* tuning knobs by name: "msm_window" (0 = auto, else 2..24), "g1_glv" (0 off, 1 on, 2 auto = on for window-sharded calls), "msm_affine_levels" (-1 auto, 0..3 batched-affine
  * tree levels before the bucket kernel; default 0), "g1_prefetch" (0|1), "g2_acc_blocks" (G2 bucket kernel variant: 2 registers,
  * 3 shared-memory accumulator built for 3 blocks/SM, 4 shared-memory accumulator at 2 blocks/SM = default), "pairing_chunks" (1..64 independent chunks of a
- * pairing batch in flight), "pairing_variant" (7 = six lanes per pairing, default; 4 = one thread per pairing), "coop_warps" (1..16 warps per block of the
+ * pairing batch in flight), "pairing_variant" (0 = chosen by batch size, default; 7 = six lanes per pairing; 4 = one thread per pairing), "coop_warps" (1..12 warps per block of the
  * six-lane pairing kernels).  Unknown key or bad value -> B200_EINVAL. */
 int b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int value);
-/* MSM tuning: window bits c (0 = automatic from n); returns previous value */
+/* MSM tuning: window bits c (0 = automatic from n, else 2..24); B200_OK or B200_EINVAL (same as set_tuning("msm_window")) */
 int b200_ctx_set_msm_window(b200_ctx *ctx, int c);
 
 /* ---- field tower, batched (diagnostic / parity surface for src/fp.rs, fp2.rs, fp6.rs, fp12.rs) - */
@@ -125,6 +130,8 @@ int b200_pairing_batch(b200_ctx *ctx, const b200_g1_affine *p, const uint8_t *p_
  * element the reference's shared-squaring loop produces (f <- f^2 * prod_t l_t is multiplicative), so
  * the limbs are bit-identical; identity terms contribute one(), like the reference's skip :566-569. */
 int b200_multi_miller_loop(b200_ctx *ctx, const b200_g1_affine *p, const uint8_t *p_inf, const b200_g2_affine *q, const uint8_t *q_inf, size_t n, b200_fp12 *out);
+/* host-pointer form of b200_pairing_product_batch_dev (see there): product i = pairs [i * terms, (i + 1) * terms) */
+int b200_pairing_product_batch(b200_ctx *ctx, const b200_g1_affine *p, const uint8_t *p_inf, const b200_g2_affine *q, const uint8_t *q_inf, size_t terms, size_t n_products, int final_exp, b200_fp12 *out);
 
 /* ---- G2Prepared (src/pairings.rs:498-546): coeffs = n x 68 x (Fp2, Fp2, Fp2) = 19 584 B per Q, in
  * the order the Miller loop consumes them; the identity is prepared as the generator (the caller keeps q_inf, :528-544).
@@ -166,7 +173,48 @@ int b200_g2_msm_shard_dev(b200_ctx *ctx, const void *points, const void *inf, co
 /* out = sum_i parts[i] (complete projective adds, src/g1.rs:161-171): combines gathered partials */
 int b200_g1_sum_dev(b200_ctx *ctx, const void *parts, size_t n, void *out);
 int b200_g2_sum_dev(b200_ctx *ctx, const void *parts, size_t n, void *out);
+
+/* ---- multi-GPU ("the ctx owns CUDA streams, scratch device memory and NCCL communicators"; §8e) ---------------
+ * (a) one process (or thread) per GPU.  Rank 0 calls b200_comm_unique_id and ships the 128 bytes to the other ranks
+ * (MPI, socket, torch.distributed ...); every rank then calls b200_ctx_comm_init on its own ctx.  After that
+ * b200_g{1,2}_msm_sharded_dev is a COLLECTIVE call (all ranks, same n, same mode): every rank computes its shard,
+ * the 144 / 288-byte partial sums are exchanged with one ncclAllGather over NVLink and added with complete additions
+ * (NCCL has no elliptic-curve reduction) — shard, collective and combine are enqueued on the ctx stream back to back,
+ * the host synchronises once at the end.  `out` (device) holds the full sum on EVERY rank.
+ *   B200_SHARD_WINDOWS: north_star's scalar-window sharding — every rank holds ALL n points and scalars and handles the
+ *                       windows w = rank (mod world).
+ *   B200_SHARD_POINTS:  every rank holds all n points/scalars too (same pointers semantics) but only READS its
+ *                       contiguous slice [rank n / world, (rank+1) n / world): all windows of a slice of the points.
+ * Pairing batches shard by pair index with no collective: the caller passes each rank its slice. */
+#define B200_COMM_ID_BYTES 128
+#define B200_SHARD_WINDOWS 0
+#define B200_SHARD_POINTS 1
+int b200_comm_unique_id(uint8_t *id /* B200_COMM_ID_BYTES */);
+int b200_ctx_comm_init(b200_ctx *ctx, const uint8_t *id /* B200_COMM_ID_BYTES */, int rank, int world);
+int b200_ctx_comm_destroy(b200_ctx *ctx);
+int b200_ctx_comm_rank(const b200_ctx *ctx);
+int b200_ctx_comm_world(const b200_ctx *ctx);
+int b200_g1_msm_sharded_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scalars, size_t n, int mode, void *out);
+int b200_g2_msm_sharded_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scalars, size_t n, int mode, void *out);
+/* (b) one process, n_gpus devices (0 = all visible): owns one ctx, one NCCL communicator (ncclCommInitAll) and one host
+ * thread per device.  b200_multi_g{1,2}_msm take HOST pointers: with B200_SHARD_POINTS (default) every device receives
+ * only its slice of the points and scalars (H2D scales with the number of GPUs), with B200_SHARD_WINDOWS all of them. */
+typedef struct b200_multi b200_multi;
+int b200_multi_create(int n_gpus, b200_multi **out);
+void b200_multi_destroy(b200_multi *m);
+int b200_multi_gpus(const b200_multi *m);
+b200_ctx *b200_multi_ctx(b200_multi *m, int i);
+int b200_multi_set_sharding(b200_multi *m, int mode);
+int b200_multi_g1_msm(b200_multi *m, const b200_g1_affine *points, const uint8_t *inf, const b200_scalar *scalars, size_t n, b200_g1_projective *out);
+int b200_multi_g2_msm(b200_multi *m, const b200_g2_affine *points, const uint8_t *inf, const b200_scalar *scalars, size_t n, b200_g2_projective *out);
+
 int b200_miller_loop_batch_dev(b200_ctx *ctx, const void *p, const void *p_inf, const void *q, const void *q_inf, size_t n, void *out);
+/* multi_miller_loop over n terms -> ONE MillerLoopResult, device pointers (src/pairings.rs:554-603) */
+int b200_multi_miller_loop_dev(b200_ctx *ctx, const void *p, const void *p_inf, const void *q, const void *q_inf, size_t n, void *out);
+/* n_products independent products of `terms` consecutive pairs each, with ONE squaring of the Miller accumulator per bit for
+ * all terms of a product (the shared-squaring loop of src/pairings.rs:554-603): out[i] = multi_miller_loop(pairs of product i)
+ * (final_exp = 0) or its final_exponentiation (final_exp = 1).  The Groth16 / BLS batch-verification shape. */
+int b200_pairing_product_batch_dev(b200_ctx *ctx, const void *p, const void *p_inf, const void *q, const void *q_inf, size_t terms, size_t n_products, int final_exp, void *out);
 int b200_final_exponentiation_batch_dev(b200_ctx *ctx, const void *in, size_t n, void *out);
 int b200_pairing_batch_dev(b200_ctx *ctx, const void *p, const void *p_inf, const void *q, const void *q_inf, size_t n, void *gt_out);
 /* out = product of the n Fp12 values (MillerLoopResult `+`, src/pairings.rs:179-186) */

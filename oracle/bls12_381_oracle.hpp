@@ -118,8 +118,24 @@ static inline Fp fp_mul(const Fp &a, const Fp &b) {
   }
   return fp_montgomery_reduce(t);
 }
-// src/fp.rs:613-660 (dedicated squaring; same value as mul(a,a))
-static inline Fp fp_square(const Fp &a) { return fp_mul(a, a); }
+// src/fp.rs:613-660: dedicated squaring — the 15 off-diagonal products a_i a_j (i < j), doubled by a one-bit shift of
+// the 12-limb intermediate, plus the six squares a_i^2 on the even limbs; same Montgomery reduction (21 mac instead of 36)
+static inline Fp fp_square(const Fp &a) {
+  u64 t[12] = {0};
+  for (int i = 0; i < 5; i++) {
+    u64 carry = 0;
+    for (int j = i + 1; j < 6; j++) t[i + j] = mac(t[i + j], a.l[i], a.l[j], carry);
+    t[i + 6] = carry;
+  }
+  for (int k = 11; k > 0; k--) t[k] = (t[k] << 1) | (t[k - 1] >> 63);
+  t[0] = 0;
+  u64 carry = 0;
+  for (int i = 0; i < 6; i++) {
+    t[2 * i] = mac(t[2 * i], a.l[i], a.l[i], carry);
+    t[2 * i + 1] = adc(t[2 * i + 1], 0, carry);
+  }
+  return fp_montgomery_reduce(t);
+}
 
 // src/fp.rs:430-484  (Longa eprint 2022/367 Alg. 2: interleaved sum of products)
 template <int T>

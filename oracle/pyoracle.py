@@ -18,10 +18,34 @@ _DIR = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_DIR, "liboracle.so")
 
 
+def _cpu_tag():
+    """CPU model + ISA flags of this machine: liboracle.so is compiled -march=native, so a copy built elsewhere (it
+    travels with the repo snapshot) must be rebuilt here"""
+    import hashlib
+    model, flags = "", ""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name") and not model:
+                model = line.split(":", 1)[1].strip()
+            elif line.startswith("flags") and not flags:
+                flags = line.split(":", 1)[1].strip()
+            if model and flags:
+                break
+    except OSError:
+        pass
+    return hashlib.sha256((model + "|" + flags).encode()).hexdigest()[:16]
+
+
 def build(force=False):
-    src = [os.path.join(_DIR, f) for f in ("oracle_capi.cpp", "bls12_381_oracle.hpp", "h2c_oracle.hpp", "h2c_constants.inc")]
-    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
-        subprocess.check_call(["make", "-C", _DIR, "-s", "liboracle.so"])
+    src = [os.path.join(_DIR, f) for f in ("oracle_capi.cpp", "bls12_381_oracle.hpp", "h2c_oracle.hpp", "h2c_constants.inc",
+                                           "Makefile")]
+    stamp = os.path.join(_DIR, "liboracle.stamp")
+    tag = _cpu_tag()
+    stale = (not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src)
+             or not os.path.exists(stamp) or open(stamp).read().strip() != tag)
+    if force or stale:
+        subprocess.check_call(["make", "-C", _DIR, "-s", "-B", "liboracle.so"])
+        open(stamp, "w").write(tag)
     return _SO
 
 
@@ -31,8 +55,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_SO):
-            build()
+        build()
         _lib = C.CDLL(_SO)
         _lib.orc_tower_op.restype = C.c_int
     return _lib

@@ -48,7 +48,7 @@ def build_cabi():
     common = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-pthread", "-Wno-unknown-pragmas", "-Wno-unused-variable",
               "-DEMUL_LAUNCH_COOPERATIVE", "-I", os.path.join(_DIR, "mock"), "-I", _DIR,
               "-I", _CSRC, "-I", os.path.join(_ROOT, "include"), "-include", os.path.join(_DIR, "cuda_host_shim.h")]
-    units = ["capi_basic.cu", "capi_msm.cu", "capi_pairing.cu", "pairing_v4.cu", "pairing_coop.cu", "capi_serial.cu",
+    units = ["capi_basic.cu", "capi_msm.cu", "capi_pairing.cu", "pairing_v4.cu", "pairing_coop.cu", "capi_multi.cu", "capi_serial.cu",
              "capi_fr.cu", "capi_h2c.cu", "capi_gt.cu"]
     from concurrent.futures import ThreadPoolExecutor
 
@@ -59,6 +59,6 @@ def build_cabi():
 
     with ThreadPoolExecutor(len(units)) as ex:
         objs = list(ex.map(one, units))
-    subprocess.check_call(["g++", "-shared", "-pthread", "-o", so] + objs)
+    subprocess.check_call(["g++", "-shared", "-pthread", "-o", so] + objs + ["-ldl"])
     open(stamp, "w").write(dg)
     return so

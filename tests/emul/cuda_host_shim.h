@@ -17,6 +17,10 @@
 #include <algorithm>   // all standard headers BEFORE the qualifier macros (libstdc++ uses __noinline__ itself)
 #include <vector>
 #include <thread>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 
 #define B200_HOST_EMUL 1
 #define __device__

@@ -51,7 +51,7 @@ def pairs(orc):
     return pxy, pinf, qxy, qinf
 
 
-@pytest.mark.parametrize("variant", [4])
+@pytest.mark.parametrize("variant", [4, 7])
 def test_variants_through_the_c_abi(eng, orc, pairs, variant):
     pxy, pinf, qxy, qinf = pairs
     eng.set_tuning("pairing_variant", variant)
@@ -62,7 +62,7 @@ def test_variants_through_the_c_abi(eng, orc, pairs, variant):
         assert np.array_equal(eng.final_exponentiation_batch(ml), orc.final_exponentiation(want_ml, threads=7))
         assert np.array_equal(eng.pairing_batch(pxy, pinf, qxy, qinf), orc.pairing(pxy, pinf, qxy, qinf, threads=7))
     finally:
-        eng.set_tuning("pairing_variant", 4)
+        eng.set_tuning("pairing_variant", 0)
 
 
 def test_product_and_prepared_paths(eng, orc, pairs):
@@ -78,7 +78,7 @@ def test_product_and_prepared_paths(eng, orc, pairs):
 
 def test_tuning_key_validation(eng):
     from bls12_381_b200 import B200Error
-    for bad in (3, 5):
+    for bad in (3, 5, 8, -1):
         with pytest.raises(B200Error):
             eng.set_tuning("pairing_variant", bad)
     with pytest.raises(B200Error):
@@ -98,8 +98,61 @@ def test_chunked_schedule(eng, orc):
     PI[700] = 1
     QI[2399] = 1
     eng.set_tuning("pairing_chunks", 3)
+    eng.set_tuning("pairing_variant", 4)        # the chunked schedule belongs to the one-thread-per-pairing kernels
     try:
         got = eng.pairing_batch(P, PI, Qx, QI)
     finally:
         eng.set_tuning("pairing_chunks", 4)
+        eng.set_tuning("pairing_variant", 0)
     assert np.array_equal(got, orc.pairing(P, PI, Qx, QI, threads=8))
+
+
+def test_six_lane_kernels_ragged_batches(eng, orc):
+    """pairing_variant 7 (pairing_coop.cu): batch sizes that are not multiples of the 5 pairs a warp takes per turn, several
+    warps per block, more warps than work, identities on either side; Miller value, final exponentiation and Gt limb-exact"""
+    rng = np.random.default_rng(17300)
+    _, pxy, pinf = util.rand_points(orc, 1, rng, 23)
+    _, qxy, qinf = util.rand_points(orc, 2, rng, 23)
+    pinf[4] = 1
+    qinf[9] = 1
+    pinf[22], qinf[22] = 1, 1
+    for warps, n in ((1, 1), (2, 6), (3, 23), (12, 11)):
+        eng.set_tuning("coop_warps", warps)
+        try:
+            a = (pxy[:n], pinf[:n], qxy[:n], qinf[:n])
+            ml = orc.miller_loop(*a, threads=8)
+            assert np.array_equal(eng.miller_loop_batch(*a), ml)
+            assert np.array_equal(eng.final_exponentiation_batch(ml), orc.final_exponentiation(ml, threads=8))
+            assert np.array_equal(eng.pairing_batch(*a), orc.pairing(*a, threads=8))
+        finally:
+            eng.set_tuning("coop_warps", 12)
+
+
+def test_shared_squaring_product_mode(eng, orc):
+    """multi_miller_loop with ONE squaring per bit for all terms (src/pairings.rs:554-603) on the six-lane kernels: a single
+    product over n terms (chunked over groups + k_coop_product fold; the mock ctx has one SM, so 24 terms already take the
+    chunked route) and batches of small products (Groth16 shape), identities skipped, with and without final exponentiation"""
+    rng = np.random.default_rng(17500)
+    n = 24
+    _, pxy, pinf = util.rand_points(orc, 1, rng, n)
+    _, qxy, qinf = util.rand_points(orc, 2, rng, n)
+    pinf[2] = 1
+    qinf[5] = 1
+    pinf[7], qinf[7] = 1, 1
+    one = np.zeros(72, np.uint64)
+    one[:6] = orc.R_LIMBS
+    eng.set_tuning("coop_warps", 2)
+    try:
+        for m in (0, 1, 2, 9, 24):
+            got = eng.multi_miller_loop(pxy[:m], pinf[:m], qxy[:m], qinf[:m]).reshape(-1)
+            want = orc.multi_miller_loop(pxy[:m], pinf[:m], qxy[:m], qinf[:m]).reshape(-1) if m else one
+            assert np.array_equal(got, want), m
+        for terms in (1, 3, 4):
+            npr = n // terms
+            a = tuple(x[:npr * terms] for x in (pxy, pinf, qxy, qinf))
+            want = np.concatenate([orc.multi_miller_loop(*(x[i * terms:(i + 1) * terms] for x in a)).reshape(1, 72)
+                                   for i in range(npr)])
+            assert np.array_equal(eng.pairing_product_batch(*a, terms, final_exp=False), want)
+            assert np.array_equal(eng.pairing_product_batch(*a, terms, final_exp=True), orc.final_exponentiation(want, threads=4))
+    finally:
+        eng.set_tuning("coop_warps", 12)

@@ -47,7 +47,7 @@ def _affine(eng, k, projs):
     return axy.cpu().numpy().view(np.uint64), ainf.cpu().numpy()
 
 
-@pytest.mark.parametrize("k,log2n", [(1, 20), (2, 18)])
+@pytest.mark.parametrize("k,log2n", [(1, 20), (2, 20)])
 def test_msm_full_size(eng, orc, k, log2n):
     n = 1 << log2n
     G = orc.G1 if k == 1 else orc.G2
@@ -94,19 +94,29 @@ def test_pairing_full_size(eng, orc):
     qxy, qinf, _, _ = _points(eng, 2, n, 778)
     dev = pxy.device
     gt = torch.empty((n, 72), dtype=torch.int64, device=dev)
+    eng.set_tuning("pairing_variant", 7)                               # six lanes per pairing at the full 2^16
     eng.pairing_batch_dev(pxy, pinf, qxy, qinf, n, gt)
-    # chunked (4 chunks on two streams) == unchunked
-    eng.set_tuning("pairing_chunks", 1)
-    gt1 = torch.empty_like(gt)
-    eng.pairing_batch_dev(pxy, pinf, qxy, qinf, n, gt1)
-    eng.set_tuning("pairing_chunks", 4)
-    assert torch.equal(gt, gt1)
-    # a random sample of pairs against the oracle, limb-exact
-    idx = np.random.default_rng(5).choice(n, 48, replace=False)
-    ti = torch.from_numpy(idx).to(dev)
-    exp = orc.pairing(pxy[ti].cpu().numpy().view(np.uint64), pinf[ti].cpu().numpy(),
-                      qxy[ti].cpu().numpy().view(np.uint64), qinf[ti].cpu().numpy(), threads=16)
-    assert np.array_equal(gt[ti].cpu().numpy().view(np.uint64), exp)
+    # ALL 2^16 pairs against the oracle, limb-exact (the oracle runs on the host cores: ~65536 x 0.7 ms / threads)
+    threads = min(64, orc.hardware_threads())
+    exp = orc.pairing(pxy.cpu().numpy().view(np.uint64), pinf.cpu().numpy(), qxy.cpu().numpy().view(np.uint64),
+                      qinf.cpu().numpy(), threads=threads)
+    assert np.array_equal(gt.cpu().numpy().view(np.uint64), exp)
+    # the one-thread-per-pairing kernels (pairing_variant 4; what the default picks at this size): chunked (4 chunks on two
+    # streams) == unchunked == variant 7 == default
+    eng.set_tuning("pairing_variant", 4)
+    try:
+        gt4 = torch.empty_like(gt)
+        eng.pairing_batch_dev(pxy, pinf, qxy, qinf, n, gt4)
+        assert torch.equal(gt, gt4)
+        eng.set_tuning("pairing_chunks", 1)
+        eng.pairing_batch_dev(pxy, pinf, qxy, qinf, n, gt4)
+        eng.set_tuning("pairing_chunks", 4)
+        assert torch.equal(gt, gt4)
+        eng.set_tuning("pairing_variant", 0)
+        eng.pairing_batch_dev(pxy, pinf, qxy, qinf, n, gt4)
+        assert torch.equal(gt, gt4)
+    finally:
+        eng.set_tuning("pairing_variant", 0)
     # product mode over the full batch: prod_i ML(p_i, q_i) then ONE final exponentiation == prod_i Gt_i on a slice
     m = 256
     ml = torch.empty((m, 72), dtype=torch.int64, device=dev)

@@ -182,9 +182,17 @@ def test_msm_medium(eng, orc, k, n):
 
 
 # ----------------------------------------------------------------------------- pairings
-def test_pairing_parity(eng, orc):
-    rng = np.random.default_rng(700)
-    n = 40
+@pytest.mark.parametrize("variant", [7, 4])      # 7 = six lanes per pairing (default), 4 = one thread per pairing
+def test_pairing_parity(eng, orc, variant):
+    eng.set_tuning("pairing_variant", variant)
+    try:
+        _pairing_parity(eng, orc, 700 + variant, 43 if variant == 7 else 40)
+    finally:
+        eng.set_tuning("pairing_variant", 0)
+
+
+def _pairing_parity(eng, orc, seed, n):
+    rng = np.random.default_rng(seed)
     _, pxy, pinf = util.rand_points(orc, 1, rng, n)
     _, qxy, qinf = util.rand_points(orc, 2, rng, n)
     pinf[1] = 1
@@ -206,6 +214,32 @@ def test_pairing_parity(eng, orc):
     one = np.zeros(72, np.uint64)
     one[:6] = orc.R_LIMBS
     assert eq(eng.multi_miller_loop(pxy[:0], None, qxy[:0], None), one)    # MillerLoopResult::default()
+
+
+def test_pairing_products_shared_squaring(eng, orc):
+    """multi_miller_loop in its reference shape — one squaring of the accumulator per bit for ALL terms (src/pairings.rs:
+    554-603) — for n in {0, 1, 2, 9, 1000} with identity terms, and batches of 3- / 4-term products (Groth16 shape)"""
+    rng = np.random.default_rng(7100)
+    n = 1000
+    _, pxy, pinf = util.rand_points(orc, 1, rng, n)
+    _, qxy, qinf = util.rand_points(orc, 2, rng, n)
+    for i in (1, 17, 500):
+        pinf[i] = 1
+    for i in (2, 17, 999):
+        qinf[i] = 1
+    one = np.zeros(72, np.uint64)
+    one[:6] = orc.R_LIMBS
+    for m in (0, 1, 2, 9, 1000):
+        got = eng.multi_miller_loop(pxy[:m], pinf[:m], qxy[:m], qinf[:m]).reshape(-1)
+        want = orc.multi_miller_loop(pxy[:m], pinf[:m], qxy[:m], qinf[:m]).reshape(-1) if m else one
+        assert eq(got, want), m
+    for terms in (3, 4):
+        npr = 60
+        a = tuple(x[:npr * terms] for x in (pxy, pinf, qxy, qinf))
+        want = np.concatenate([orc.multi_miller_loop(*(x[i * terms:(i + 1) * terms] for x in a)).reshape(1, 72)
+                               for i in range(npr)])
+        assert eq(eng.pairing_product_batch(*a, terms, final_exp=False), want)
+        assert eq(eng.pairing_product_batch(*a, terms, final_exp=True), orc.final_exponentiation(want, threads=8))
 
 
 def test_gt_generator_kat_on_gpu(eng, orc):

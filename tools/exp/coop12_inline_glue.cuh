@@ -1,13 +1,14 @@
 // Lane-cooperative Fp12 arithmetic for the pairing kernels (pairing_coop.cu).
 //
-// One pairing is worked on by a GROUP of 6 consecutive lanes of a warp (5 groups per warp; lanes 30/31 exit at once).  An Fp12 element is held as a degree-5 polynomial in w over Fp2,
+// One pairing is worked on by a GROUP of 6 consecutive lanes of a warp (5 groups per warp, lanes 30/31 shadow group 0
+// and never store).  An Fp12 element is held as a degree-5 polynomial in w over Fp2,
 //     X = x_0 + x_1 w + ... + x_5 w^5,   w^6 = xi = 1 + u,
 // lane k of the group keeping the ONE coefficient x_k (24 registers).  In terms of the reference's structs
 // (src/fp12.rs:11-14, src/fp6.rs:9-13; Fp12 = Fp6[w]/(w^2 - v), Fp6 = Fp2[v]/(v^3 - xi)):  x_{2j} = c0.c_j,
 // x_{2j+1} = c1.c_j.  Nothing of an Fp12 ever lives in local memory: operands are exchanged through a small
 // shared-memory BOARD per group (24 slots of one Fp2), every lane computes one output coefficient as a dot product of
 // Fp2 values with LAZY reduction (all partial products accumulated as unreduced 768-bit integers, two Montgomery
-// reductions per coefficient), and the lanes of a group stay in step with __syncwarp(mask of the group).
+// reductions per coefficient), and the lanes of a group stay in step with __syncwarp().
 //
 // Every function returns canonical field elements, so results are bit-identical to src/fp12.rs Mul :197 / square
 // :174 / mul_by_014 :116 / frobenius_map :145 / conjugate :136 / invert :187 and src/pairings.rs cyclotomic_square :66.
@@ -30,20 +31,24 @@ constexpr int CO_BOARD = CO_SLOT * CO_NSLOT;    // words per group
 constexpr int CO_WARP_SMEM = CO_GROUPS * CO_BOARD * 4;  // bytes of shared memory per warp
 
 struct cgrp {
-  uint32_t *bd;    // this group's board (shared memory)
-  int k;           // coefficient index of this lane, 0..5
-  unsigned mask;   // the six lanes of this group: groups synchronise independently (lanes 30/31 of a warp exit at once)
+  uint32_t *bd;  // this group's board (shared memory)
+  int k;         // coefficient index of this lane, 0..5
+  bool live;     // false for lanes 30/31: they run the same instruction stream on group 0's board but never write to it
 };
 
-B200_DEV void co_sync(const cgrp &g) { __syncwarp(g.mask); }
+B200_DEV void co_sync() { __syncwarp(); }
 B200_DEV uint32_t *co_slot(const cgrp &g, int s) { return g.bd + CO_SLOT * s; }
 B200_DEV fp co_ld(const uint32_t *p) { return fp_load(p); }
 B200_DEV fp2 co_ld2(const uint32_t *p) { return fp2{fp_load(p), fp_load(p + 12)}; }
 B200_DEV void co_put(const cgrp &g, int s, const fp2 &a) {
-  fp_store(co_slot(g, s), a.c0);
-  fp_store(co_slot(g, s) + 12, a.c1);
+  if (g.live) {
+    fp_store(co_slot(g, s), a.c0);
+    fp_store(co_slot(g, s) + 12, a.c1);
+  }
 }
-B200_DEV void co_put_half(const cgrp &g, int s, int half, const fp &a) { fp_store(co_slot(g, s) + 12 * half, a); }
+B200_DEV void co_put_half(const cgrp &g, int s, int half, const fp &a) {
+  if (g.live) fp_store(co_slot(g, s) + 12 * half, a);
+}
 B200_DEV int co_mod6(int i) { return i < 0 ? i + 6 : (i >= 6 ? i - 6 : i); }
 B200_DEV int co_mod3(int i) { return i < 0 ? i + 3 : (i >= 3 ? i - 3 : i); }
 
@@ -104,12 +109,12 @@ B200_NOINL fp2 co_mul(cgrp g, fp2 x, fp2 y) {
   co_put(g, CS_F + g.k, x);
   co_put(g, CS_G + g.k, y);
   co_put(g, CS_GX + g.k, fp2_mul_by_nonresidue(y));
-  co_sync(g);
+  co_sync();
   const int k = g.k;
   const uint32_t *bd = g.bd;
   fp2 z = co_dot<6>([=](int t) { return bd + CO_SLOT * (CS_F + co_mod6(k - t)); },
                     [=](int t) { return bd + CO_SLOT * ((t > k ? CS_GX : CS_G) + t); });
-  co_sync(g);
+  co_sync();
   return z;
 }
 
@@ -121,7 +126,7 @@ B200_NOINL fp2 co_sqr(cgrp g, fp2 x) {
   const int k = g.k, c = k >> 1, par = k & 1;
   const uint32_t *bd = g.bd;
   co_put(g, CS_F + k, x);
-  co_sync(g);
+  co_sync();
   if (par) {
     co_put(g, S_RX1 + c, fp2_mul_by_nonresidue(x));  // xi * B_c
   } else {
@@ -133,7 +138,7 @@ B200_NOINL fp2 co_sqr(cgrp g, fp2 x) {
     co_put(g, S_R2 + c, q);
     co_put(g, S_RX2 + c, fp2_mul_by_nonresidue(q));
   }
-  co_sync(g);
+  co_sync();
   fp2 m = co_dot<3>(
       [=](int t) {
         int li = co_mod3(c - t);
@@ -143,9 +148,9 @@ B200_NOINL fp2 co_sqr(cgrp g, fp2 x) {
         bool wrap = t > c;
         return bd + CO_SLOT * (par ? (wrap ? S_RX1 + t : CS_F + 2 * t + 1) : (wrap ? S_RX2 + t : S_R2 + t));
       });
-  co_sync(g);
+  co_sync();
   co_put(g, CS_F + k, m);  // odd slots: M1_c
-  co_sync(g);
+  co_sync();
   fp2 r;
   if (par) {
     r = fp2_dbl(m);
@@ -154,7 +159,7 @@ B200_NOINL fp2 co_sqr(cgrp g, fp2 x) {
     fp2 vm1 = c == 0 ? fp2_mul_by_nonresidue(co_ld2(bd + CO_SLOT * (CS_F + 5))) : co_ld2(bd + CO_SLOT * (CS_F + k - 1));
     r = fp2_sub(fp2_sub(m, m1), vm1);
   }
-  co_sync(g);
+  co_sync();
   return r;
 }
 
@@ -167,14 +172,14 @@ B200_NOINL fp2 co_mul_sparse(cgrp g, fp2 x, const uint32_t *pc0, const uint32_t 
   const uint32_t *bd = g.bd;
   co_put(g, CS_F + k, x);
   co_put(g, S_FX + k, fp2_mul_by_nonresidue(x));
-  co_sync(g);
+  co_sync();
   fp2 z = co_dot<3>(
       [=](int t) {
         int s = t == 0 ? CS_F + k : (t == 1 ? (k < 2 ? S_FX : CS_F) + co_mod6(k - 2) : (k < 3 ? S_FX : CS_F) + co_mod6(k - 3));
         return bd + CO_SLOT * s;
       },
       [=](int t) { return t == 0 ? pc0 : (t == 1 ? pc1 : pc4); });
-  co_sync(g);
+  co_sync();
   return z;
 }
 
@@ -186,7 +191,7 @@ B200_NOINL fp2 co_cyclotomic_sqr(cgrp g, fp2 x) {
   const int k = g.k;
   const uint32_t *bd = g.bd;
   co_put(g, CS_F + k, x);
-  co_sync(g);
+  co_sync();
   const bool alane = k < 3;
   fp2 y = co_ld2(bd + CO_SLOT * (CS_F + co_mod6(k + 3)));
   fp2 s = fp2_add(x, y);
@@ -196,7 +201,7 @@ B200_NOINL fp2 co_cyclotomic_sqr(cgrp g, fp2 x) {
   fp h = fp_mul_c(hu, hv);  // a-lane: re (a+b)^2, b-lane: im (a+b)^2
   co_put(g, S_T + k, own);
   co_put_half(g, S_H + (alane ? k : k - 3), alane ? 0 : 1, h);
-  co_sync(g);
+  co_sync();
   // which pair feeds lane k, and how (z-names of the reference: x0=z0, x3=z1, x1=z2, x4=z3, x2=z4, x5=z5):
   //   x0 <- 3 c0(0) - 2 x0, x3 <- 3 c1(0) + 2 x3, x2 <- 3 c0(1) - 2 x2, x5 <- 3 c1(1) + 2 x5, x1 <- 3 xi c1(2) + 2 x1, x4 <- 3 c0(2) - 2 x4
   const int q = k == 0 || k == 3 ? 0 : (k == 2 || k == 5 ? 1 : 2);
@@ -211,7 +216,7 @@ B200_NOINL fp2 co_cyclotomic_sqr(cgrp g, fp2 x) {
   }
   fp2 d = use_c0 ? fp2_sub(c, x) : fp2_add(c, x);
   fp2 r = fp2_add(fp2_dbl(d), c);
-  co_sync(g);
+  co_sync();
   return r;
 }
 
@@ -221,9 +226,10 @@ B200_NOINL fp2 co_frobenius(cgrp g, fp2 x, int n) {
   co_put(g, CS_F + g.k, v);   // own slot, read back by this lane only
   const uint32_t *pa = g.bd + CO_SLOT * (CS_F + g.k);
   const uint32_t *pb = &K_FROBW[6 * (n - 1) + g.k][0];
-  co_sync(g);
+  if (!g.live) pa = pb;       // shadow lanes never wrote their slot
+  co_sync();
   fp2 z = co_dot<1>([=](int) { return pa; }, [=](int) { return pb; });
-  co_sync(g);
+  co_sync();
   return z;
 }
 B200_DEV fp2 co_conj(const cgrp &g, const fp2 &x) { return (g.k & 1) ? fp2_neg(x) : x; }
@@ -240,12 +246,12 @@ B200_NOINL fp2 co_inv(cgrp g, fp2 x, const uint32_t *pow2) {
   // squares of the two Fp6 halves
   co_put(g, CS_F + k, x);
   co_put(g, S_FX + k, fp2_mul_by_nonresidue(x));
-  co_sync(g);
+  co_sync();
   fp2 sq = co_dot<3>([=](int t) { return bd + CO_SLOT * (CS_F + 2 * co_mod3(c - t) + par); },
                      [=](int t) { return bd + CO_SLOT * ((t > c ? S_FX : CS_F) + 2 * t + par); });
-  co_sync(g);
+  co_sync();
   co_put(g, CS_F + k, sq);
-  co_sync(g);
+  co_sync();
   // T = A^2 - v B^2
   fp2 vb = c == 0 ? fp2_mul_by_nonresidue(co_ld2(bd + CO_SLOT * (CS_F + 5))) : co_ld2(bd + CO_SLOT * (CS_F + 2 * c - 1));
   fp2 T = fp2_sub(co_ld2(bd + CO_SLOT * (CS_F + 2 * c)), vb);
@@ -253,7 +259,7 @@ B200_NOINL fp2 co_inv(cgrp g, fp2 x, const uint32_t *pow2) {
     co_put(g, S_T + c, T);
     co_put(g, S_TX + c, fp2_mul_by_nonresidue(T));
   }
-  co_sync(g);
+  co_sync();
   // Fp6 inverse of T = (T0, T1, T2): c'_0 = T0 T0 - (xi T1) T2, c'_1 = (xi T2) T2 - T0 T1, c'_2 = T1 T1 - T0 T2
   const int s1a = c == 0 ? S_T + 0 : (c == 1 ? S_TX + 2 : S_T + 1), s1b = c == 0 ? S_T + 0 : (c == 1 ? S_T + 2 : S_T + 1);
   const int s2a = c == 0 ? S_TX + 1 : S_T + 0, s2b = c == 1 ? S_T + 1 : S_T + 2;
@@ -261,7 +267,7 @@ B200_NOINL fp2 co_inv(cgrp g, fp2 x, const uint32_t *pow2) {
   fp2 p2a = co_ld2(bd + CO_SLOT * s2a), p2b = co_ld2(bd + CO_SLOT * s2b);
   fp2 cp = fp2_sub(M2(p1a, p1b), M2(p2a, p2b));
   if (!par) co_put(g, S_C + c, cp);
-  co_sync(g);
+  co_sync();
   // N = T0 c'_0 + xi (T1 c'_2 + T2 c'_1), computed by every lane
   fp2 N = fp2_add(M2(co_ld2(bd + CO_SLOT * S_T), co_ld2(bd + CO_SLOT * S_C)),
                   fp2_mul_by_nonresidue(fp2_add(M2(co_ld2(bd + CO_SLOT * (S_T + 1)), co_ld2(bd + CO_SLOT * (S_C + 2))),
@@ -269,16 +275,16 @@ B200_NOINL fp2 co_inv(cgrp g, fp2 x, const uint32_t *pow2) {
   fp ni = fp_inv_fast(fp_add(fp_sqr_c(N.c0), fp_sqr_c(N.c1)), pow2);
   fp2 Ninv{fp_mul_c(N.c0, ni), fp_mul_c(N.c1, fp_neg(ni))};
   fp2 ti = M2(cp, Ninv);  // (T^-1)_c
-  co_sync(g);
+  co_sync();
   co_put(g, CS_F + k, x);
   if (!par) {
     co_put(g, S_TI + c, ti);
     co_put(g, S_T + c, fp2_mul_by_nonresidue(ti));
   }
-  co_sync(g);
+  co_sync();
   fp2 r = co_dot<3>([=](int t) { return bd + CO_SLOT * (CS_F + 2 * co_mod3(c - t) + par); },
                     [=](int t) { return bd + CO_SLOT * ((t > c ? S_T : S_TI) + t); });
-  co_sync(g);
+  co_sync();
   return par ? fp2_neg(r) : r;
 }
 
