@@ -269,8 +269,10 @@ class Bench:
             self.eng.comm_init(bytes(uid.cpu().numpy().tobytes()), self.rank, self.world)
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)      # > 126 MB L2
         self.peak = self.peak_ms = None
+        self.peak_lohi = None
         if self.rank == 0:
             self.peak, self.peak_ms = self.eng.imad_peak(3000)
+            self.peak_lohi, _ = self.eng.imad_peak(3000, mode=1)     # the same products as separate IMAD + IMAD.HI.U32
         self.traffic = load_traffic()
 
     def close(self):
@@ -477,8 +479,11 @@ class Bench:
                     base = "k_msm_accumulate"           # G1 / G2-register / G2-shared-memory variants of the bucket kernel
                 per_kernel.setdefault(base, []).append(ms)
             dom = DOMINANT[wl]
+            chunked_v4 = False
             if wl == "pairing" and dom not in per_kernel:
-                dom = "k_final_exp"                      # pairing_variant = 4 (one thread per pairing)
+                # one-thread-per-pairing kernels (what the default picks above 28 672 pairs): Miller loop and final exponentiation
+                # run as 4 chunks on two streams, so their event times overlap — the roofline is taken over the whole step
+                dom, chunked_v4 = "k_final_exp", True
             ksum = {kname: sum(v) for kname, v in per_kernel.items()}
             tot_k = sum(ksum.values()) or 1.0
             if dom in per_kernel:
@@ -503,8 +508,9 @@ class Bench:
                     fpm = fpm_exec = 16020.0 * n_local
                     alg_bytes = (96 + 192 + 576) * n_local
                 else:
-                    fpm = fpm_exec = 9104.0 * n_local                       # final exponentiation kernel
-                    alg_bytes = 576 * 2 * n_local
+                    fpm = fpm_exec = 16020.0 * n_local                      # k_miller_loop + k_final_exp together (whole step)
+                    alg_bytes = (96 + 192 + 576) * n_local
+                    avg_ms = ms_per_step
                 achieved = fpm * IMAD_PER_FPM / (avg_ms * 1e-3)
                 try:
                     hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -512,11 +518,17 @@ class Bench:
                 except Exception:
                     hbm_peak, hbm_of = 6650.0, "fallback"
                 tr = self.traffic.get("%s_2p%d" % (wl, log2n)) if world == 1 else None
-                roof = {"bound": "int (IMAD.WIDE.U32 pipe; SURVEY 8d: not hbm, not tensor)", "kernel": dom,
+                roof = {"bound": "int (IMAD.WIDE.U32 pipe; SURVEY 8d: not hbm, not tensor)",
+                        "kernel": "k_miller_loop + k_final_exp (4 chunks on two streams; whole step)" if chunked_v4 else dom,
                         "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "T IMAD32/s", "frac": achieved / peak,
                         "executed_frac": fpm_exec * IMAD_PER_FPM / (avg_ms * 1e-3) / peak,
                         "peak_source": "b200_imad_peak microbenchmark run live on this GPU (%.2f ms, dependent-free IMAD.WIDE.U32; "
                                        "SASS + ncu of the microbenchmark: profiles/r02_imad_peak.txt)" % self.peak_ms,
+                        "peak_detail": {"imad_wide_u32_per_s": peak, "imad_lo_plus_imad_hi_pairs_per_s": self.peak_lohi,
+                                        "per_clock_per_sm_at_sampled_clock": (peak / (148 * clocks["sm_mhz"] * 1e6) if clocks.get("sm_mhz") else None),
+                                        "sm_mhz": clocks.get("sm_mhz"),
+                                        "note": "one 32x32+64 multiply-add = one IMAD.WIDE.U32 (a carry-linked mad.lo.cc/madc.hi pair is "
+                                                "fused into it by ptxas); as separate IMAD + IMAD.HI.U32 it costs two multiplier issues"},
                         "model": "SURVEY 8d cost sheet x 300 IMAD32 per FpM", "kernel_ms_per_step": avg_ms,
                         "kernel_launches_per_step": len(per_kernel[dom]) / steps,
                         # share of the SUMMED kernel time (kernels of an MSM overlap on three streams), not of the step

@@ -27,6 +27,7 @@ SIGNATURES = {
     "b200_tower_op": [_vp, _i, _i, _vp, _vp, _vp, _sz],
     "b200_glv_decompose": [_vp, _vp, _sz, _vp, _vp],
     "b200_imad_peak": [_vp, _i, C.POINTER(C.c_double), C.POINTER(C.c_double)],
+    "b200_imad_peak_mode": [_vp, _i, _i, C.POINTER(C.c_double), C.POINTER(C.c_double)],
     "b200_gt_mul_batch": [_vp, _vp, _vp, _sz, _vp],
     "b200_gt_mul_batch_dev": [_vp, _vp, _vp, _sz, _vp],
     "b200_fr_op": [_vp, _i, _vp, _vp, _sz, _vp],

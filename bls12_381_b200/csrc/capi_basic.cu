@@ -214,6 +214,41 @@ __global__ void __launch_bounds__(256) k_imad_peak(int iters, uint64_t *sink) {
   if (x == 0x1234567ull) sink[0] = x;  // never true in practice; keeps the chain alive
 }
 
+// the two halves of the product as separate instructions: mad.lo + mad.hi per product (two multiplier instructions per
+// 32x32 -> 64 product; without the carry link between the halves it is not even a full 64-bit accumulate).  Audit of the roofline denominator: shows whether the wide form is the cheapest way
+// to a 64-bit product on sm_100a.  Counted in the same unit (one 32x32+64 multiply-add per lo/hi PAIR).
+__global__ void __launch_bounds__(256) k_imad_peak_lohi(int iters, uint64_t *sink) {
+  uint32_t lo[8], hi[8];
+  uint32_t a = threadIdx.x * 2654435761u + 12345u, b = blockIdx.x * 40503u + 977u;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    lo[k] = k * 0x9e3779b9u + threadIdx.x;
+    hi[k] = k * 0x7f4a7c15u + blockIdx.x;
+  }
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+#ifdef B200_HOST_EMUL
+        uint64_t t = (uint64_t)(a + k) * (b + r);
+        lo[k] += (uint32_t)t;
+        hi[k] += (uint32_t)(t >> 32);
+#else
+        // (a carry-linked mad.lo.cc / madc.hi pair is fused by ptxas into ONE IMAD.WIDE.U32 — which is how fp_mul gets its wide
+        // multiply-adds; the unlinked pair below stays two instructions, IMAD + IMAD.HI.U32)
+        asm volatile("mad.lo.u32 %0, %2, %3, %0;\n\tmad.hi.u32 %1, %2, %3, %1;" : "+r"(lo[k]), "+r"(hi[k]) : "r"(a + k), "r"(b + r));
+#endif
+      }
+    }
+  }
+  uint32_t x = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) x ^= lo[k] ^ hi[k];
+  if (x == 0x1234567u) sink[0] = x;
+}
+
 inline unsigned nblk(size_t n, unsigned b) { return (unsigned)((n + b - 1) / b); }
 
 template <class F>
@@ -405,6 +440,11 @@ int b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int value) {
   } else if (!strcmp(key, "g1_glv")) {
     if (value < 0 || value > 2) return B200_EINVAL;
     ctx->tune_g1_glv = value;
+  } else if (!strcmp(key, "msm_tail_groups")) {
+    ctx->tune_msm_tail_groups = value != 0;
+  } else if (!strcmp(key, "msm_reduce")) {
+    if (value < -1 || value > 2) return B200_EINVAL;
+    ctx->tune_msm_reduce = value;
   } else if (!strcmp(key, "g1_prefetch")) {
     ctx->tune_g1_prefetch = value != 0;
   } else if (!strcmp(key, "pairing_variant")) {
@@ -587,8 +627,11 @@ GROUP_API(g2, fp2, b200_g2_affine, b200_g2_projective)
 
 // ================================================================ measurement helper
 int b200_imad_peak(b200_ctx *ctx, int iters, double *imad_per_sec, double *ms_out) {
+  return b200_imad_peak_mode(ctx, iters, 0, imad_per_sec, ms_out);
+}
+int b200_imad_peak_mode(b200_ctx *ctx, int iters, int mode, double *imad_per_sec, double *ms_out) {
   CHECK_CTX(ctx);
-  if (iters <= 0 || !imad_per_sec) return B200_EINVAL;
+  if (iters <= 0 || !imad_per_sec || mode < 0 || mode > 1) return B200_EINVAL;
   int rc = arena_reserve(ctx, 256);
   if (rc != B200_OK) return rc;
   uint64_t *sink = arena_take<uint64_t>(ctx, 1);
@@ -596,9 +639,17 @@ int b200_imad_peak(b200_ctx *ctx, int iters, double *imad_per_sec, double *ms_ou
   B200_CUDA(ctx, cudaEventCreate(&e0));
   B200_CUDA(ctx, cudaEventCreate(&e1));
   unsigned grid = (unsigned)ctx->sm_count * 8, block = 256;
-  B200_LAUNCH(ctx, k_imad_peak, grid, block, 0, iters / 8 + 1, sink);  // warm-up
+  if (mode == 0) {
+    B200_LAUNCH(ctx, k_imad_peak, grid, block, 0, iters / 8 + 1, sink);  // warm-up
+  } else {
+    B200_LAUNCH(ctx, k_imad_peak_lohi, grid, block, 0, iters / 8 + 1, sink);
+  }
   B200_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
-  B200_LAUNCH(ctx, k_imad_peak, grid, block, 0, iters, sink);
+  if (mode == 0) {
+    B200_LAUNCH(ctx, k_imad_peak, grid, block, 0, iters, sink);
+  } else {
+    B200_LAUNCH(ctx, k_imad_peak_lohi, grid, block, 0, iters, sink);
+  }
   B200_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
   B200_CUDA(ctx, cudaEventSynchronize(e1));
   float ms = 0;

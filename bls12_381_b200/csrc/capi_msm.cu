@@ -30,6 +30,8 @@
 
 using namespace b200;
 
+int b200i_msm_check(b200_ctx *ctx);
+
 namespace {
 
 constexpr int MAX_WINDOWS = 128;
@@ -94,13 +96,27 @@ __device__ __forceinline__ void for_each_digit(const msm_plan &pl, const uint32_
   walk_digits(pl, v, ENT_PHI | (g.neg2 ? ENT_NEG : 0u), f);
 }
 
+// q (src/scalar.rs:76-81), 32-bit little-endian words: the ABI takes Scalar::to_bytes(), i.e. canonical scalars < q
+__device__ __constant__ const uint32_t FR_Q[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
+                                                  0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+__device__ __forceinline__ bool scalar_ge_q(const uint32_t s[8]) {
+  for (int k = 7; k >= 0; k--) {
+    if (s[k] != FR_Q[k]) return s[k] > FR_Q[k];
+  }
+  return true;
+}
+
+// `bad` (first window group only): set when a scalar is >= q.  The signed-window recoding and the GLV split assume
+// canonical input (the carry out of the top window is dropped when c divides 256); instead of returning a wrong point for raw
+// 32-byte strings the call fails with B200_EINVAL.
 __global__ void __launch_bounds__(256) k_msm_count(msm_plan pl, const uint32_t *scalars, const uint8_t *inf, size_t n,
-                                                 uint32_t *hist) {
+                                                 uint32_t *hist, uint32_t *bad) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (inf && inf[i]) return;
   uint32_t s[8];
   load_scalar(s, scalars, i);
+  if (bad != nullptr && scalar_ge_q(s)) *bad = 1u;
   for_each_digit(pl, s, [&](int j, uint32_t b, uint32_t) { atomicAdd(&hist[(size_t)j * pl.nbuckets + b], 1u); });
 }
 
@@ -483,12 +499,75 @@ __global__ void __launch_bounds__(BLOCK) k_msm_reduce(int nbuckets, int chunk, c
   if (threadIdx.x == 0) proj_store<F>(partials + PB * ((size_t)j * gridDim.x + blockIdx.x), proj_load<F>(smem));
 }
 
+// ---- lane-cooperative bucket reduction (round 2).  k_msm_reduce above gives every THREAD a chunk of buckets: ~60 dependent
+// complete additions of ~13 us each (a single thread cannot keep more than one multiplier busy) — 0.8 ms per window group,
+// the exposed tail of every MSM and the limiter of multi-GPU strong scaling.  Here a GROUP of six lanes (curve_warp.cuh:
+// the independent products of a formula level in different lanes, ~1.7 us per addition) owns a chunk, five groups per warp.
+//   k_msm_reduce_coop   group g of window j: run = sum B_b, acc = sum (b - lo + 1) B_b over its chunk [lo, lo + chunk), then
+//                       acc += lo * run by a fixed-length double-and-add (uniform control flow: full-mask shuffles)
+//   k_msm_fold_coop     sums `per` consecutive partials per group, until few enough are left for the Horner kernel
+template <class F, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) k_msm_reduce_coop(int nbuckets, int chunk, int groups_per_window, int lo_bits,
+                                                               const char *buckets, char *partials) {
+  constexpr size_t PB = 3 * field_traits<F>::bytes;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int grp = lane / 6;
+  const bool live = grp < 5;
+  if (!live) grp = 0;
+  const int sub = live ? lane - 6 * grp : lane - 30, base = live ? 6 * grp : 30;
+  const int j = blockIdx.y;
+  int gi = (blockIdx.x * WARPS + warp) * 5 + grp;
+  const bool active = live && gi < groups_per_window;
+  if (gi >= groups_per_window) gi = groups_per_window - 1;
+  const int lo = gi * chunk;
+  const char *wb = buckets + PB * (size_t)j * nbuckets;
+  proj<F> run = proj_identity<F>(), acc = proj_identity<F>();
+#pragma unroll 1
+  for (int t = chunk - 1; t >= 0; t--) {
+    int b = lo + t;
+    proj<F> bk = b < nbuckets ? proj_load<F>(wb + PB * b) : proj_identity<F>();
+    run = grp_add(run, bk, sub, base);
+    acc = grp_add(acc, run, sub, base);
+  }
+  // bucket b is worth (b + 1): acc so far counts (b - lo + 1); add lo * run (MSB first, every group the same number of steps)
+  proj<F> t = proj_identity<F>();
+#pragma unroll 1
+  for (int bit = lo_bits - 1; bit >= 0; bit--) {
+    t = grp_double(t, sub, base);
+    proj<F> t2 = grp_add(t, run, sub, base);
+    t = proj_select(t, t2, ((lo >> bit) & 1) != 0);
+  }
+  acc = grp_add(acc, t, sub, base);
+  if (active && sub == 0) proj_store<F>(partials + PB * ((size_t)j * groups_per_window + gi), acc);
+}
+template <class F, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) k_msm_fold_coop(int n_in, int per, int n_out, const char *in, char *out) {
+  constexpr size_t PB = 3 * field_traits<F>::bytes;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int grp = lane / 6;
+  const bool live = grp < 5;
+  if (!live) grp = 0;
+  const int sub = live ? lane - 6 * grp : lane - 30, base = live ? 6 * grp : 30;
+  const int j = blockIdx.y;
+  int gi = (blockIdx.x * WARPS + warp) * 5 + grp;
+  const bool active = live && gi < n_out;
+  if (gi >= n_out) gi = n_out - 1;
+  proj<F> acc = proj_identity<F>();
+#pragma unroll 1
+  for (int t = 0; t < per; t++) {
+    int i = gi * per + t;
+    proj<F> v = i < n_in ? proj_load<F>(in + PB * ((size_t)j * n_in + i)) : proj_identity<F>();
+    acc = grp_add(acc, v, sub, base);
+  }
+  if (active && sub == 0) proj_store<F>(out + PB * ((size_t)j * n_out + gi), acc);
+}
+
 // Horner over the windows, one GROUP of windows per launch, top window first, on the ctx's side stream:
 // while the (one-thread, latency-bound) chain  acc <- 2^(c*gap) * acc + S_w  of the upper windows runs,
 // the bucket kernels of the lower windows keep all SMs busy on the main stream; only the last group's
 // step is exposed.  Lanes j < cnt first sum the per-block partials of local window (j_top - j).
-// `prev_w` = global index of the window processed last (-1: none yet); `final_shift` = doublings*c to apply
-// after the group's lowest window (only for the last group of a shard whose lowest window is not 0).
+// `prev_w` = global index of the window processed last (-1: none yet); `final_shift` = doublings to apply after the group's
+// lowest window: down to the next group's top window, or (last group) down to bit 0 of the shard's lowest window.
 template <class F>
 __global__ void __launch_bounds__(32) k_msm_horner(msm_plan pl, int j_top, int cnt, int prev_w, int final_shift,
                                                  int parts_per_window, const char *partials, char *hacc) {
@@ -503,7 +582,9 @@ __global__ void __launch_bounds__(32) k_msm_horner(msm_plan pl, int j_top, int c
 #pragma unroll 1
     for (int k = 0; k < parts_per_window; k++)
       sw = warp_add(sw, proj_load<F>(partials + PB * ((size_t)j * parts_per_window + k)), lane);
-    if (prev_w >= 0) {
+    // the doublings from the previous GROUP's lowest window down to this group's top window were already applied at the end
+    // of the previous launch (tail_shift), while this group's buckets were still being accumulated and reduced
+    if (prev_w >= 0 && i > 0) {
 #pragma unroll 1
       for (int k = (prev_w - w) * pl.c; k > 0; k--) acc = warp_double(acc, lane);
     }
@@ -522,6 +603,19 @@ __global__ void k_store_identity(char *out) {
 
 inline unsigned nblk(size_t n, unsigned b) { return (unsigned)((n + b - 1) / b); }
 
+// is window width c a good choice for n points?  The scalars have 255 bits: the TOP window holds tb = 255 - c*floor(255/c)
+// of them, i.e. only 2^tb distinct digits with n / 2^tb points each.  That is fine when the window is (almost) full, when
+// those buckets are so heavy that the block-parallel giant path takes them (>= GIANT_BUCKET points), or when they are not
+// much heavier than an ordinary bucket — but in between a handful of THREADS walk hundreds of points each
+// (measured: 2^17 points, c = 13, tb = 8: 256 buckets of 512 points, bucket kernel 8.8 ms instead of 2.0 ms with c = 14).
+// tb = 0 (c divides 255 = 3 * 5 * 17) is the worst case: the signed-digit carry of the full top window opens one more
+// window whose single bucket collects half of all points.
+bool window_ok(int c, size_t n) {
+  int tb = 255 - c * (255 / c);
+  if (tb == 0) return false;
+  size_t heavy = n >> tb, avg = n >> (c - 1);
+  return tb >= c - 2 || heavy >= GIANT_BUCKET || heavy <= 4 * avg + 8;
+}
 int auto_window(size_t n) {
   // minimise  W * n (bucket adds) + W * 2^(c-1) * ~3 (reduction) ; measured sweet spots on B200
   int lg = 0;
@@ -529,6 +623,11 @@ int auto_window(size_t n) {
   int c = lg - 4;
   if (c < 4) c = 4;
   if (c > 16) c = 16;
+  const int order[4] = {0, 1, -1, 2};
+  for (int k = 0; k < 4; k++) {
+    int cc = c + order[k];
+    if (cc >= 4 && cc <= 18 && window_ok(cc, n)) return cc;
+  }
   return c;
 }
 
@@ -548,6 +647,7 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
   pl.nbuckets = 1 << (pl.c - 1);
   pl.nloc = 0;
   for (int w = shard; w < pl.nwin; w += n_shards) pl.win[pl.nloc++] = w;
+  ctx->msm_bad_flag = nullptr;
   if (n == 0 || pl.nloc == 0) {
     B200_LAUNCH(ctx, k_store_identity<F>, 1, 32, 0, (char *)out);
     return B200_OK;
@@ -560,11 +660,29 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
   int chunk = (pl.nbuckets + chunks - 1) / chunks;
   if (chunk < 1) chunk = 1;
   int blocks_per_window = chunks / RB;
+  // lane-cooperative reduction (default): groups of six lanes own RCHUNK buckets; partial counts per level: G, G/16, ... <= 8
+  // tune_msm_reduce: 0 never, 1 only where the reduction is EXPOSED (the last window group of a call), 2 every group,
+  // -1 (default) = 1 for G1, 2 for G2.  Measured at 2^20 on one GPU: G1 8.99 (0) / 9.63 (2) ms — the cooperative kernels do more
+  // total work and compete with the pipe-bound bucket kernel of the next group; G2 30.1 (0) / 26.1 (2) ms.
+  const int reduce_mode = ctx->tune_msm_reduce >= 0 ? ctx->tune_msm_reduce : (sizeof(F) == sizeof(fp) ? 1 : 2);
+  const bool coop_reduce = reduce_mode != 0;
+  constexpr int RCHUNK = 16, RFOLD = 16, RWARPS = 4;
+  int r_chunk = pl.nbuckets < RCHUNK ? pl.nbuckets : RCHUNK, r_lo_bits = 0;
+  while ((1 << r_lo_bits) < pl.nbuckets) r_lo_bits++;
+  int r_n[6], r_levels = 0;
+  r_n[r_levels++] = (pl.nbuckets + r_chunk - 1) / r_chunk;
+  while (r_n[r_levels - 1] > 8 && r_levels < 6) {
+    r_n[r_levels] = (r_n[r_levels - 1] + RFOLD - 1) / RFOLD;
+    r_levels++;
+  }
+  size_t r_bytes = 0;
+  for (int l = 0; l < r_levels; l++) r_bytes += arena_pad((size_t)pl.nloc * r_n[l] * PB);
   // at most (entries of the largest group) / GIANT_BUCKET giants can exist at once
   const uint32_t max_giants = (uint32_t)((size_t)pl.nloc * sstride / GIANT_BUCKET + pl.nloc);
   size_t need = 4 * arena_pad(total * 4) + 3 * arena_pad(4 * SIZE_BINS * 4) + arena_pad((size_t)pl.nloc * sstride * 4) +
                 arena_pad(total * PB) + arena_pad((size_t)pl.nloc * blocks_per_window * PB) + arena_pad(PB) +
-                (pl.glv ? arena_pad(48 * n) : 0) + arena_pad((size_t)max_giants * GIANT_PARTS * PB) + 4096;
+                (pl.glv ? arena_pad(48 * n) : 0) + arena_pad((size_t)max_giants * GIANT_PARTS * PB) + 4096 + 256 +
+                (coop_reduce ? r_bytes : 0);
   if (ctx->tune_msm_affine_levels != 0) {  // upper bound of the affine-level scratch (largest group <= all local windows)
     need += 8 * arena_pad(total * 4) + 3 * 256;
     for (int l = 1; l <= 3; l++) need += arena_pad((size_t)pl.nloc * ((sstride >> l) + pl.nbuckets + 8) * 2 * field_traits<F>::bytes);
@@ -581,9 +699,26 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
   char *buckets = arena_take<char>(ctx, total * PB);
   char *partials = arena_take<char>(ctx, (size_t)pl.nloc * blocks_per_window * PB);
   char *hacc = arena_take<char>(ctx, PB);
+  char *r_buf[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (coop_reduce)
+    for (int l = 0; l < r_levels; l++) r_buf[l] = arena_take<char>(ctx, (size_t)pl.nloc * r_n[l] * PB);
   char *bx = pl.glv ? arena_take<char>(ctx, 48 * n) : nullptr;
   char *gparts = arena_take<char>(ctx, (size_t)max_giants * GIANT_PARTS * PB);
-  if (pl.glv) B200_LAUNCH(ctx, k_msm_glv_bx, nblk(n, 256), 256, 0, (const char *)points, n, bx);
+  uint32_t *bad = arena_take<uint32_t>(ctx, 1);
+  ctx->msm_bad_flag = bad;
+  B200_CUDA(ctx, cudaMemsetAsync(bad, 0, sizeof(uint32_t), ctx->stream));
+  auto wait_points = [&]() -> int {   // msm_host: the points arrive on stream3 (ev_sync[30]); nothing before this reads them
+    if (ctx->msm_points_event_pending) {
+      ctx->msm_points_event_pending = false;
+      B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_sync[30], 0));
+    }
+    return B200_OK;
+  };
+  if (pl.glv) {
+    int rcw = wait_points();
+    if (rcw != B200_OK) return rcw;
+    B200_LAUNCH(ctx, k_msm_glv_bx, nblk(n, 256), 256, 0, (const char *)points, n, bx);
+  }
   // hist and cursor are adjacent: one memset
   B200_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)((char *)offsets - (char *)hist), ctx->stream));
   // Window groups, top-down.  A group = consecutive local windows = a contiguous range of slots.
@@ -614,8 +749,12 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
       gsz[ng++] = left - left / 2 - (left >= 6 ? 1 : 0); left -= gsz[ng - 1];
       if (left >= 3) { gsz[ng++] = left - 1; left = 1; }
       gsz[ng++] = left;
+    } else if (ctx->tune_msm_tail_groups && left >= 2) {
+      // one window per group: the top window's reduction and its long run of Horner doublings (pre-applied at the end of its
+      // launch) overlap the bucket accumulation of the windows below — what a window shard of an 8-GPU MSM needs
+      while (left > 0) { gsz[ng++] = 1; left--; }
     } else {
-      gsz[ng++] = left;   // (splitting 2-3 windows into [n-1, 1] was measured slower: 3.2-4.0 vs 2.5-3.5 ms per shard)
+      gsz[ng++] = left;   // (round 1, slow reduction: splitting 2-3 windows into [n-1, 1] was slower: 3.2-4.0 vs 2.5-3.5 ms per shard)
     }
   }
   // scratch of the affine levels, sized for the largest group and reused by every group (main stream only)
@@ -665,7 +804,8 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
     pg.nloc = cnt;
     for (int i = 0; i < cnt; i++) pg.win[i] = pl.win[j_lo + i];
     size_t s0 = (size_t)j_lo * pl.nbuckets;
-    B200_LAUNCH_ON(ctx, st, k_msm_count, nblk(n, 256), 256, 0, pg, (const uint32_t *)scalars, (const uint8_t *)inf, n, hist + s0);
+    B200_LAUNCH_ON(ctx, st, k_msm_count, nblk(n, 256), 256, 0, pg, (const uint32_t *)scalars, (const uint8_t *)inf, n, hist + s0,
+                   st == ctx->stream ? bad : (uint32_t *)nullptr);   // checked once, by the first group (main stream)
     B200_LAUNCH_ON(ctx, st, k_msm_scan, cnt, 1024, 0, pl.nbuckets, hist + s0, offsets + s0);
     B200_LAUNCH_ON(ctx, st, k_msm_scatter, nblk(n, 256), 256, 0, pg, (const uint32_t *)scalars, (const uint8_t *)inf, n,
                    sstride, offsets + s0, cursor + s0, sorted + (size_t)j_lo * sstride);
@@ -680,6 +820,10 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
     int cnt = gsz[g], j_lo = j_top - cnt + 1;
     size_t s0 = (size_t)j_lo * pl.nbuckets, gtotal = (size_t)cnt * pl.nbuckets;
     if (g > 0) B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_sync[20 + g], 0));  // sort(g) done on stream2
+    if (g == 0) {
+      int rcw = wait_points();   // the bucket kernels are the first to read the points
+      if (rcw != B200_OK) return rcw;
+    }
     // per-group scheduling scratch: SIZE_BINS-sized arrays are double-buffered by group parity
     uint32_t *sh = size_hist + (size_t)(g & 1) * 2 * SIZE_BINS, *sc = sh + SIZE_BINS;
     uint32_t *sb = size_base + (size_t)(g & 1) * SIZE_BINS;
@@ -747,15 +891,30 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
       B200_CUDA(ctx, cudaEventRecord(ctx->ev_sync[20 + g + 1], ctx->stream2));
     }
     B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_sync[1 + 2 * g], 0));
-    dim3 rgrid(blocks_per_window, cnt);
-    B200_LAUNCH_ON(ctx, ctx->stream2, (k_msm_reduce<F, RB>), rgrid, RB, RB * PB, pl.nbuckets, chunk, buckets + PB * s0,
-                   partials + PB * (size_t)j_lo * blocks_per_window);
+    const bool coop_here = reduce_mode == 2 || (reduce_mode == 1 && g == ng - 1);
+    if (coop_here) {
+      dim3 g0((unsigned)((r_n[0] + 5 * RWARPS - 1) / (5 * RWARPS)), cnt);
+      B200_LAUNCH_ON(ctx, ctx->stream2, (k_msm_reduce_coop<F, RWARPS>), g0, 32 * RWARPS, 0, pl.nbuckets, r_chunk, r_n[0], r_lo_bits,
+                     buckets + PB * s0, r_buf[0] + PB * (size_t)j_lo * r_n[0]);
+      for (int l = 1; l < r_levels; l++) {
+        dim3 gl((unsigned)((r_n[l] + 5 * RWARPS - 1) / (5 * RWARPS)), cnt);
+        B200_LAUNCH_ON(ctx, ctx->stream2, (k_msm_fold_coop<F, RWARPS>), gl, 32 * RWARPS, 0, r_n[l - 1], RFOLD, r_n[l],
+                       r_buf[l - 1] + PB * (size_t)j_lo * r_n[l - 1], r_buf[l] + PB * (size_t)j_lo * r_n[l]);
+      }
+    } else {
+      dim3 rgrid(blocks_per_window, cnt);
+      B200_LAUNCH_ON(ctx, ctx->stream2, (k_msm_reduce<F, RB>), rgrid, RB, RB * PB, pl.nbuckets, chunk, buckets + PB * s0,
+                     partials + PB * (size_t)j_lo * blocks_per_window);
+    }
     B200_CUDA(ctx, cudaEventRecord(ctx->ev_sync[2 + 2 * g], ctx->stream2));
     B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream3, ctx->ev_sync[2 + 2 * g], 0));
     bool last = g == ng - 1;
-    int final_shift = last ? pl.win[0] * pl.c : 0;
+    // doublings applied at the END of this launch: down to bit 0 after the last group, else down to the next group's top
+    // window (so that the next launch starts with an addition as soon as its window sums exist)
+    int final_shift = last ? pl.win[0] * pl.c : (pl.win[j_lo] - pl.win[j_lo - 1]) * pl.c;
     B200_LAUNCH_ON(ctx, ctx->stream3, k_msm_horner<F>, 1, 32, 0, pl, j_top, cnt, prev_w, final_shift,
-                   blocks_per_window, partials, hacc);
+                   coop_here ? r_n[r_levels - 1] : blocks_per_window,
+                   coop_here ? (const char *)r_buf[r_levels - 1] : (const char *)partials, hacc);
     prev_w = pl.win[j_lo];
     j_top = j_lo - 1;
   }
@@ -773,19 +932,41 @@ int msm_host(b200_ctx *ctx, const void *points, const uint8_t *inf, const void *
   void *dp = stage_take(ctx, AB * n), *ds = stage_take(ctx, 32 * n), *di = inf ? stage_take(ctx, n) : nullptr;
   void *dout = stage_take(ctx, PB);
   if (n) {
-    B200_CUDA(ctx, cudaMemcpyAsync(dp, points, AB * n, cudaMemcpyHostToDevice, ctx->stream));
+    // scalars (and flags) first, on the main stream: the window digits / counting sort need nothing else.  The points —
+    // three (G1) or six (G2) times as many bytes — follow on stream3 and overlap the sort; the bucket kernel waits for them.
+    B200_CUDA(ctx, cudaEventRecord(ctx->ev_sync[31], ctx->stream));               // earlier users of the staging buffer
+    B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream3, ctx->ev_sync[31], 0));
     B200_CUDA(ctx, cudaMemcpyAsync(ds, scalars, 32 * n, cudaMemcpyHostToDevice, ctx->stream));
     if (inf) B200_CUDA(ctx, cudaMemcpyAsync(di, inf, n, cudaMemcpyHostToDevice, ctx->stream));
+    B200_CUDA(ctx, cudaMemcpyAsync(dp, points, AB * n, cudaMemcpyHostToDevice, ctx->stream3));
+    B200_CUDA(ctx, cudaEventRecord(ctx->ev_sync[30], ctx->stream3));
+    ctx->msm_points_event_pending = true;
   }
   rc = msm_dev<F>(ctx, dp, di, ds, n, 0, 1, dout);
+  if (ctx->msm_points_event_pending) {   // msm_dev left before its first bucket kernel: keep the ordering anyway
+    ctx->msm_points_event_pending = false;
+    cudaStreamWaitEvent(ctx->stream, ctx->ev_sync[30], 0);
+  }
   if (rc != B200_OK) return rc;
   B200_CUDA(ctx, cudaMemcpyAsync(out, dout, PB, cudaMemcpyDeviceToHost, ctx->stream));
   B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return B200_OK;
+  return b200i_msm_check(ctx);
 }
 
 }  // namespace
 
+// after the stream has been synchronised: did the last MSM of this ctx see a non-canonical scalar?
+int b200i_msm_check(b200_ctx *ctx) {
+  if (ctx->msm_bad_flag == nullptr) return B200_OK;
+  uint32_t bad = 0;
+  B200_CUDA(ctx, cudaMemcpyAsync(&bad, ctx->msm_bad_flag, sizeof(bad), cudaMemcpyDeviceToHost, ctx->stream));
+  B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (bad) {
+    snprintf(ctx->err, sizeof(ctx->err), "MSM: a scalar is not canonical (>= q); the ABI takes Scalar::to_bytes()");
+    return B200_EINVAL;
+  }
+  return B200_OK;
+}
 // enqueue-only MSM (shard of the windows) for capi_multi.cu (no lock, no synchronisation)
 int b200i_msm_enqueue(b200_ctx *ctx, int k, const void *points, const void *inf, const void *scalars, size_t n, int shard,
                       int n_shards, void *out) {
@@ -807,7 +988,7 @@ int b200_g1_msm_shard_dev(b200_ctx *ctx, const void *points, const void *inf, co
   int rc = msm_dev<fp>(ctx, points, inf, scalars, n, shard, n_shards, out);
   if (rc != B200_OK) return rc;
   B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return B200_OK;
+  return b200i_msm_check(ctx);
 }
 int b200_g2_msm_shard_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scalars, size_t n, int shard,
                           int n_shards, void *out) {
@@ -816,7 +997,7 @@ int b200_g2_msm_shard_dev(b200_ctx *ctx, const void *points, const void *inf, co
   int rc = msm_dev<fp2>(ctx, points, inf, scalars, n, shard, n_shards, out);
   if (rc != B200_OK) return rc;
   B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return B200_OK;
+  return b200i_msm_check(ctx);
 }
 int b200_glv_decompose(b200_ctx *ctx, const b200_scalar *scalars, size_t n, uint8_t *k1k2, uint8_t *signs) {
   CHECK_CTX(ctx);

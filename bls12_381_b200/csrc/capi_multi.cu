@@ -25,6 +25,7 @@ using namespace b200;
 int b200i_msm_enqueue(b200_ctx *ctx, int k, const void *points, const void *inf, const void *scalars, size_t n, int shard,
                       int n_shards, void *out);
 int b200i_sum_enqueue(b200_ctx *ctx, int k, const void *parts, size_t n, void *out);
+int b200i_msm_check(b200_ctx *ctx);   // after a stream synchronisation: B200_EINVAL when the last MSM saw a scalar >= q
 
 namespace {
 
@@ -176,15 +177,24 @@ int multi_msm(b200_multi *m, const void *points, const uint8_t *inf, const void 
     void *dp = stage_take(c, AB * cnt), *ds = stage_take(c, 32 * cnt), *di = inf ? stage_take(c, cnt) : nullptr;
     void *dout = stage_take(c, PB);
     if (cnt) {
-      B200_CUDA(c, cudaMemcpyAsync(dp, (const char *)points + AB * lo, AB * cnt, cudaMemcpyHostToDevice, c->stream));
+      // scalars first (main stream), points on stream3 under the counting sort — same schedule as the one-GPU b200_g1_msm
+      B200_CUDA(c, cudaEventRecord(c->ev_sync[31], c->stream));
+      B200_CUDA(c, cudaStreamWaitEvent(c->stream3, c->ev_sync[31], 0));
       B200_CUDA(c, cudaMemcpyAsync(ds, (const char *)scalars + 32 * lo, 32 * cnt, cudaMemcpyHostToDevice, c->stream));
       if (inf) B200_CUDA(c, cudaMemcpyAsync(di, inf + lo, cnt, cudaMemcpyHostToDevice, c->stream));
+      B200_CUDA(c, cudaMemcpyAsync(dp, (const char *)points + AB * lo, AB * cnt, cudaMemcpyHostToDevice, c->stream3));
+      B200_CUDA(c, cudaEventRecord(c->ev_sync[30], c->stream3));
+      c->msm_points_event_pending = true;
     }
     char *parts = c->comm_buf, *mine = parts + PB * w;
     if (mode == B200_SHARD_POINTS)
       r = b200i_msm_enqueue(c, K, dp, di, ds, cnt, 0, 1, w > 1 ? (void *)mine : dout);
     else
       r = b200i_msm_enqueue(c, K, dp, di, ds, cnt, d, w, w > 1 ? (void *)mine : dout);
+    if (c->msm_points_event_pending) {
+      c->msm_points_event_pending = false;
+      cudaStreamWaitEvent(c->stream, c->ev_sync[30], 0);
+    }
     if (r != B200_OK) return r;
     if (w > 1) {
       int nrc = nccl().AllGather(mine, parts, PB, NCCL_UINT8, (nccl_comm)c->nccl_comm, c->stream);
@@ -196,7 +206,7 @@ int multi_msm(b200_multi *m, const void *points, const uint8_t *inf, const void 
     }
     if (d == 0) B200_CUDA(c, cudaMemcpyAsync(out, dout, PB, cudaMemcpyDeviceToHost, c->stream));
     B200_CUDA(c, cudaStreamSynchronize(c->stream));
-    return B200_OK;
+    return b200i_msm_check(c);
   });
   return rc;
 }
@@ -255,7 +265,7 @@ int b200_g1_msm_sharded_dev(b200_ctx *ctx, const void *points, const void *inf, 
   int rc = msm_sharded_enqueue(ctx, 1, points, inf, scalars, n, mode, out);
   if (rc != B200_OK) return rc;
   B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return B200_OK;
+  return b200i_msm_check(ctx);
 }
 int b200_g2_msm_sharded_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scalars, size_t n, int mode,
                             void *out) {
@@ -264,7 +274,7 @@ int b200_g2_msm_sharded_dev(b200_ctx *ctx, const void *points, const void *inf, 
   int rc = msm_sharded_enqueue(ctx, 2, points, inf, scalars, n, mode, out);
   if (rc != B200_OK) return rc;
   B200_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return B200_OK;
+  return b200i_msm_check(ctx);
 }
 
 int b200_multi_create(int n_gpus, b200_multi **out) {

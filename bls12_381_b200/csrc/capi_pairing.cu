@@ -68,8 +68,8 @@ int pairing_dev(b200_ctx *ctx, const void *p, const void *pi, const void *q, con
   // that a single launch per kernel is already one (partial) wave, and smaller launches only add latency
   if (n <= (size_t)ctx->sm_count * 4 * 64 + 2048) chunks = 1;
   if (chunks == 1) {
-    int rc = miller_dev(ctx, p, pi, q, qi, n, out);
-    return rc != B200_OK ? rc : final_exp_dev(ctx, out, n, out);
+    int rc = b200_pair_miller_v4(ctx, ctx->stream, p, pi, q, qi, n, out);
+    return rc != B200_OK ? rc : b200_pair_final_exp_v4(ctx, ctx->stream, out, n, out);
   }
   B200_CUDA(ctx, cudaEventRecord(ctx->ev_sync[0], ctx->stream));
   B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_sync[0], 0));
@@ -88,8 +88,10 @@ int pairing_dev(b200_ctx *ctx, const void *p, const void *pi, const void *q, con
     const char *cp = (const char *)p + 96 * lo, *cq = (const char *)q + 192 * lo;
     const uint8_t *cpi = pi ? (const uint8_t *)pi + lo : nullptr, *cqi = qi ? (const uint8_t *)qi + lo : nullptr;
     char *co = (char *)out + 576 * lo;
-    int rc = miller_on(ctx, st, cp, cpi, cq, cqi, cnt, co);
-    if (rc == B200_OK) rc = final_exp_on(ctx, st, co, cnt, co);
+    // the chunked two-stream schedule belongs to the one-thread-per-pairing kernels: call them directly (the dispatchers
+    // would pick the six-lane kernels for a chunk-sized batch, and those use the ctx arena, which two streams cannot share)
+    int rc = b200_pair_miller_v4(ctx, st, cp, cpi, cq, cqi, cnt, co);
+    if (rc == B200_OK) rc = b200_pair_final_exp_v4(ctx, st, co, cnt, co);
     if (rc != B200_OK) return rc;
   }
   return B200_OK;

@@ -22,6 +22,10 @@ struct b200_ctx {
   char err[256] = {0};
   uint64_t launches = 0;
   int msm_c = 0;
+  // host-pointer MSM: the point upload runs on stream3 while the scalars (uploaded first) are being sorted on the main
+  // stream; the first kernel that reads points waits for ev_sync[30] when this is set (msm_host in capi_msm.cu)
+  bool msm_points_event_pending = false;
+  uint32_t *msm_bad_flag = nullptr;   // device word set by the MSM digit kernel when a scalar is not canonical (>= q)
   // G1 MSM: GLV split k = k1 + k2*lambda (8 windows of 2n entries instead of 16 of n).  0 off (default), 1 on,
   // 2 = on for window-sharded calls only.  Implemented, parity-tested, and measured NEGATIVE at 2^20 on B200:
   // 1 GPU 9.34 vs 9.02 ms, 8 GPUs 3.66 vs 3.19 ms — halving the windows halves the (window x bucket) slots, i.e. the
@@ -34,6 +38,16 @@ struct b200_ctx {
   // same time instead of overlapping it with other warps' multiplications, and batches large enough to amortise it
   // (K >= 128 pairs per thread) leave too few threads at this size.  Groundwork for larger N.
   int tune_msm_affine_levels = 0;
+  // bucket reduction: 0 = one thread per chunk of buckets (round 1), 1 = lane-cooperative (six lanes per chunk, round 2) for
+  // the last — exposed — window group only, 2 = lane-cooperative for every group, -1 = by curve (G1: 1, G2: 2).  The CPU test
+  // harness defaults to 0 (every shuffle is two fiber barriers there: the emulated cooperative reduction costs minutes) and
+  // switches it on for one small case (tests/test_msm_on_mock_cpu.py::test_cooperative_bucket_reduction).
+#ifdef B200_HOST_EMUL
+  int tune_msm_reduce = 0;
+#else
+  int tune_msm_reduce = -1;
+#endif
+  int tune_msm_tail_groups = 1;  // 2-3 local windows (window shards of a multi-GPU MSM): one window per group (1) or one group (0)
   int tune_g1_prefetch = 1;    // G1 bucket kernel: cp.async double-buffered prefetch of the next point (1) or plain loads (0)
   int tune_pairing_chunks = 4; // independent Miller+final-exp chunks of a pairing batch kept in flight on 2 streams
   // G2 bucket kernel: 2 = accumulator in registers (255 regs, 2 blocks/SM); 3 = accumulator in shared memory, built

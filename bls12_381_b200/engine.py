@@ -105,9 +105,10 @@ class Engine:
         nm = names.value.decode().split("\n")
         return [(nm[i], float(ms[i])) for i in range(min(n, max_records)) if i < len(nm) and nm[i]]
 
-    def imad_peak(self, iters=2000):
+    def imad_peak(self, iters=2000, mode=0):
+        """mode 0: mad.wide.u32 streams (the roofline denominator); 1: the same product as a mad.lo.cc / madc.hi pair"""
         v, ms = C.c_double(), C.c_double()
-        self._ck(self.lib.b200_imad_peak(self.h, iters, C.byref(v), C.byref(ms)), "imad_peak")
+        self._ck(self.lib.b200_imad_peak_mode(self.h, iters, mode, C.byref(v), C.byref(ms)), "imad_peak")
         return v.value, ms.value
 
     # ---------------------------------------------------------------- field tower (parity surface)

@@ -11,12 +11,15 @@
 //   pairing(&G1Affine,&G2Affine)->Gt   src/pairings.rs:607  pairing_batch(engine, ps, qs)
 //   multi_miller_loop(&[(&p,&q)])      src/pairings.rs:554  multi_miller_loop(engine, ps, qs)
 //   MillerLoopResult::final_exponentiation :48              MillerLoopResult::final_exponentiation(engine)
+//   products of pairings (Groth16 / BLS batch verification)  pairing_products(engine, ps, qs, terms)
+//   Gt ==, +, -, double, identity       src/pairings.rs:228-337   Gt::operator==, add, neg, dbl, identity
 //
 // Value types are byte-compatible with the reference's in-memory values (Montgomery limbs), `Copy`-like
 // PODs; fallible calls throw b200::Error carrying the ABI's code and text instead of Rust's CtOption/panic
 // (batch_normalize keeps the reference's `assert_eq!(p.len(), q.len())`, src/g1.rs:807, as an exception).
 #pragma once
 #include <cstdint>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -199,7 +202,28 @@ inline std::vector<G2Projective> hash_to_curve_g2(const Engine &e, const std::ve
 }
 
 struct Gt {
-  b200_fp12 v;  // canonical Fp12 (src/pairings.rs:211)
+  b200_fp12 v;  // canonical Fp12 (src/pairings.rs:211): limbs identical to the crate's Gt.0, so == is bytewise
+  bool operator==(const Gt &o) const { return std::memcmp(&v, &o.v, sizeof v) == 0; }
+  bool operator!=(const Gt &o) const { return !(*this == o); }
+  // Gt::identity() = Fp12::one()  (src/pairings.rs:228-231)
+  static Gt identity() {
+    Gt g;
+    std::memset(&g.v, 0, sizeof g.v);
+    const uint64_t one[6] = {0x760900000002fffdull, 0xebf4000bc40c0002ull, 0x5f48985753c758baull,
+                             0x77ce585370525745ull, 0x5c071a97a256ec6dull, 0x15f65ec3fa80e493ull};  // R = 2^384 mod p
+    std::memcpy(g.v.c[0].l, one, sizeof one);
+    return g;
+  }
+  // the group law of Gt is multiplication in Fp12: a + b (src/pairings.rs:270-276), -a = conjugate (:253-259), double (:233-236)
+  static Gt tower(const Engine &e, int op, const Gt &a, const Gt *b) {
+    Gt out;
+    e.check(b200_tower_op(e.raw(), 12, op, reinterpret_cast<const uint64_t *>(&a.v), b ? reinterpret_cast<const uint64_t *>(&b->v) : nullptr,
+                          reinterpret_cast<uint64_t *>(&out.v), 1), "tower_op");
+    return out;
+  }
+  Gt add(const Engine &e, const Gt &o) const { return tower(e, B200_OP_MUL, *this, &o); }
+  Gt neg(const Engine &e) const { return tower(e, B200_OP_CONJUGATE, *this, nullptr); }
+  Gt dbl(const Engine &e) const { return tower(e, B200_OP_SQUARE, *this, nullptr); }
   // out[i] = &g[i] * &scalars[i]   (src/pairings.rs:296-323)
   static std::vector<Gt> mul_batch(const Engine &e, const std::vector<Gt> &g, const std::vector<Scalar> &scalars) {
     if (g.size() != scalars.size()) throw Error(B200_EINVAL, "Gt::mul_batch: length mismatch");
@@ -255,6 +279,21 @@ inline MillerLoopResult multi_miller_loop(const Engine &e, const std::vector<G1A
   MillerLoopResult out;
   e.check(b200_multi_miller_loop(e.raw(), pxy.data(), pinf.data(), qxy.data(), qinf.data(), ps.size(), &out.v),
           "multi_miller_loop");
+  return out;
+}
+
+// n_products independent products of `terms` consecutive pairs each — the shape of Groth16 / BLS batch verification:
+//   (0..n).map(|i| multi_miller_loop(&terms[i]).final_exponentiation())   with ONE squaring per bit shared by the terms of a
+// product (src/pairings.rs:554-603), ps.size() == qs.size() == terms * n_products
+inline std::vector<Gt> pairing_products(const Engine &e, const std::vector<G1Affine> &ps, const std::vector<G2Affine> &qs, size_t terms) {
+  if (terms == 0 || ps.size() % terms != 0) throw Error(B200_EINVAL, "pairing_products: the number of pairs must be a multiple of terms");
+  std::vector<b200_g1_affine> pxy;
+  std::vector<b200_g2_affine> qxy;
+  std::vector<uint8_t> pinf, qinf;
+  detail::split(ps, qs, pxy, pinf, qxy, qinf);
+  std::vector<Gt> out(ps.size() / terms);
+  e.check(b200_pairing_product_batch(e.raw(), pxy.data(), pinf.data(), qxy.data(), qinf.data(), terms, out.size(), 1, &out.data()->v),
+          "pairing_product_batch");
   return out;
 }
 

@@ -75,7 +75,7 @@ uint64_t b200_ctx_launch_count(const b200_ctx *ctx);
 int b200_ctx_set_timing(b200_ctx *ctx, int on);
 int b200_ctx_get_timing(b200_ctx *ctx, char *names, size_t names_len, float *ms, int max);
 /* tuning knobs by name: "msm_window" (0 = auto, else 2..24), "g1_glv" (0 off, 1 on, 2 auto = on for window-sharded calls), "msm_affine_levels" (-1 auto, 0..3 batched-affine
- * tree levels before the bucket kernel; default 0), "g1_prefetch" (0|1), "g2_acc_blocks" (G2 bucket kernel variant: 2 registers,
+ * tree levels before the bucket kernel; default 0), "g1_prefetch" (0|1), "msm_reduce" (bucket reduction: 0 one thread per chunk, 1 lane-cooperative for the last window group, 2 for every group, -1 by curve = default), "msm_tail_groups" (0|1), "g2_acc_blocks" (G2 bucket kernel variant: 2 registers,
  * 3 shared-memory accumulator built for 3 blocks/SM, 4 shared-memory accumulator at 2 blocks/SM = default), "pairing_chunks" (1..64 independent chunks of a
  * pairing batch in flight), "pairing_variant" (0 = chosen by batch size, default; 7 = six lanes per pairing; 4 = one thread per pairing), "coop_warps" (1..12 warps per block of the
  * six-lane pairing kernels).  Unknown key or bad value -> B200_EINVAL. */
@@ -283,6 +283,9 @@ int b200_fr_hash_to_field(b200_ctx *ctx, const uint8_t *msgs, const uint64_t *of
 /* ---- measurement helper: dependent-free IMAD.WIDE.U32 stream on all SMs; returns achieved
  * 32x32+64 multiply-adds per second (the integer roofline denominator) ------------ */
 int b200_imad_peak(b200_ctx *ctx, int iters, double *imad_per_sec, double *ms);
+/* mode 0 = the above (mad.wide.u32 -> IMAD.WIDE.U32); mode 1 = the same 64-bit multiply-accumulate as a mad.lo.cc / madc.hi
+ * pair (two multiplier instructions per product), counted in the same unit — the audit of the roofline denominator */
+int b200_imad_peak_mode(b200_ctx *ctx, int iters, int mode, double *imad_per_sec, double *ms_out);
 
 #ifdef __cplusplus
 }

@@ -216,6 +216,26 @@ def _pairing_parity(eng, orc, seed, n):
     assert eq(eng.multi_miller_loop(pxy[:0], None, qxy[:0], None), one)    # MillerLoopResult::default()
 
 
+def test_msm_rejects_non_canonical_scalars(eng, orc):
+    """Scalar::to_bytes() is canonical (< q): raw strings >= q are refused (B200_EINVAL), q - 1 is fine"""
+    from bls12_381_b200 import B200Error
+    rng = np.random.default_rng(7200)
+    n = 300
+    q = pyref.Q
+    for k in (1, 2):
+        _, xy, inf = util.rand_points(orc, k, rng, n)
+        s = util.rand_scalars(rng, n)
+        for bad in (q, q + 7, (1 << 256) - 1):
+            s2 = s.copy()
+            s2[123] = np.frombuffer(bad.to_bytes(32, "little"), np.uint8)
+            with pytest.raises(B200Error):
+                eng.msm(k, xy, inf, s2)
+        s2 = s.copy()
+        s2[123] = np.frombuffer((q - 1).to_bytes(32, "little"), np.uint8)
+        G = orc.G1 if k == 1 else orc.G2
+        assert eq(G.to_affine(eng.msm(k, xy, inf, s2))[0], G.to_affine(G.msm_pippenger(xy, inf, s2, c=8, threads=8))[0])
+
+
 def test_pairing_products_shared_squaring(eng, orc):
     """multi_miller_loop in its reference shape — one squaring of the accumulator per bit for ALL terms (src/pairings.rs:
     554-603) — for n in {0, 1, 2, 9, 1000} with identity terms, and batches of 3- / 4-term products (Groth16 shape)"""

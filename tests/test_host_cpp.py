@@ -20,6 +20,13 @@ int main() {
   (void)ntt_fn;
   auto h2c_fn = &hash_to_curve_g2;   // hash-to-curve surface
   (void)h2c_fn;
+  // the pairing half of the boundary (INTEGRATION.md §3b): batch pairing, multi_miller_loop, products, Gt group law
+  auto pb_fn = &pairing_batch;
+  auto mml_fn = &multi_miller_loop;
+  auto pp_fn = &pairing_products;
+  auto gadd_fn = &Gt::add;
+  (void)pb_fn; (void)mml_fn; (void)pp_fn; (void)gadd_fn;
+  if (!(Gt::identity() == Gt::identity()) || Gt::identity().v.c[0].l[0] != 0x760900000002fffdull) return 4;
   try {
     Engine e(0);
     std::vector<G1Projective> p(2);

@@ -112,3 +112,32 @@ def test_window_sharding_and_sum(eng, orc, data):
     assert eng.lib.b200_g1_sum_dev(eng.h, parts.ctypes.data, 2, out.ctypes.data) == 0
     want = orc.G1.msm_naive(xy[:n], inf[:n], s[:n], threads=4)
     assert np.array_equal(orc.G1.to_affine(out)[0], orc.G1.to_affine(want)[0])
+
+
+def test_non_canonical_scalar_is_rejected(eng, orc, data):
+    """the ABI takes Scalar::to_bytes() (canonical, < q): a raw 32-byte string >= q makes the call fail with B200_EINVAL
+    instead of returning a wrong point (the signed-window recoding drops the carry out of the top window)"""
+    from bls12_381_b200 import B200Error
+    xy, inf, s = data[1]
+    q = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+    for bad in (q, q + 5, (1 << 256) - 1):
+        s2 = s[:9].copy()
+        s2[4] = np.frombuffer(bad.to_bytes(32, "little"), np.uint8)
+        with pytest.raises(B200Error):
+            eng.msm(1, xy[:9], inf[:9], s2)
+    s2 = s[:9].copy()
+    s2[4] = np.frombuffer((q - 1).to_bytes(32, "little"), np.uint8)          # the largest canonical scalar is fine
+    GP._msm_case(eng, orc, 1, xy[:9], inf[:9], s2, cs=(0,))
+
+
+def test_cooperative_bucket_reduction(eng, orc, data):
+    """msm_reduce = 1 (k_msm_reduce_coop / k_msm_fold_coop: six lanes per bucket chunk, fixed-length offset multiply, folds),
+    the default on hardware, on the fiber scheduler: one G1 case with a window wide enough for a fold level (the G2
+    instantiation of the same templates runs in the -m gpu suite)"""
+    eng.set_tuning("msm_reduce", 2)
+    try:
+        for k in (1,):
+            xy, inf, s = data[k]
+            GP._msm_case(eng, orc, k, xy[:20], inf[:20], s[:20], cs=(9,))        # 2^8 buckets: 16 chunks -> one fold level
+    finally:
+        eng.set_tuning("msm_reduce", 0)
