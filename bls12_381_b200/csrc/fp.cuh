@@ -330,6 +330,8 @@ B200_DEV fp fp_add_nr(const fp &a, const fp &b) {
 //   REDC(t) = REDC(t_low) + t_high, and REDC(t_low) is the interleaved multiplier run with b = 1:
 //   row 0 contributes a*1, rows 1..11 only reduce and shift (the shift is an add-with-carry chain on the
 //   otherwise idle ALU pipe; the IMAD pipe sees 12 x 12 + 12 = 156 multiplies).
+B200_DEV void fp_redc_wide_step(uint32_t *A, uint32_t *B);
+B200_DEV fp fp_redc_wide_tail(const uint32_t *ev, const uint32_t *od, const fpw &t);
 B200_DEV fp fp_redc_wide(const fpw &t) {
   uint32_t ev[12], od[12];
 #pragma unroll
@@ -342,40 +344,11 @@ B200_DEV fp fp_redc_wide(const fpw &t) {
   fp_redc_step(ev, od);
 #pragma unroll
   for (int i = 1; i < 12; i += 2) {
-    // roles as in fp_mul: A = od (aligned at word 0 after the shift), B = ev (shifted in by two words)
-    ptx_add_cc(od[0], od[0], ev[1]);
-#pragma unroll
-    for (int k = 0; k < 10; k++) ptx_addc_cc(ev[k], ev[k + 2], 0u);
-    ptx_addc_cc(ev[10], 0u, 0u);
-    ev[11] = 0;
-    fp_redc_step(od, ev);
-    if (i + 1 < 12) {
-      ptx_add_cc(ev[0], ev[0], od[1]);
-#pragma unroll
-      for (int k = 0; k < 10; k++) ptx_addc_cc(od[k], od[k + 2], 0u);
-      ptx_addc_cc(od[10], 0u, 0u);
-      od[11] = 0;
-      fp_redc_step(ev, od);
-    }
+    fp_redc_wide_step(od, ev);  // roles as in fp_mul: A = od (aligned at word 0 after the shift), B = ev (shifted in by two words)
+    if (i + 1 < 12) fp_redc_wide_step(ev, od);
   }
   // q_low = (od >> 32) + ev ; result = q_low + t_high, then one conditional subtraction
-  fp r;
-  ptx_add_cc(r.v[0], ev[0], od[1]);
-#pragma unroll
-  for (int k = 1; k < 11; k++) ptx_addc_cc(r.v[k], ev[k], od[k + 1]);
-  ptx_addc(r.v[11], ev[11], 0u);
-  ptx_add_cc(r.v[0], r.v[0], t.v[12]);
-#pragma unroll
-  for (int k = 1; k < 11; k++) ptx_addc_cc(r.v[k], r.v[k], t.v[12 + k]);
-  ptx_addc(r.v[11], r.v[11], t.v[23]);
-  uint32_t d[12], borrow;
-  ptx_sub_cc(d[0], r.v[0], fp_modw(0));
-#pragma unroll
-  for (int k = 1; k < 12; k++) ptx_subc_cc(d[k], r.v[k], fp_modw(k));
-  ptx_subc(borrow, 0u, 0u);
-#pragma unroll
-  for (int k = 0; k < 12; k++) r.v[k] = borrow ? r.v[k] : d[k];
-  return r;
+  return fp_redc_wide_tail(ev, od, t);
 }
 // acc[0..2*len) += x[0], x[2], .., x[2*(len-1)] * s as one carry chain; the carry goes into acc[2*len] when TOP
 template <int LEN, bool TOP>
@@ -482,14 +455,23 @@ B200_DEV fpw3 fp_mul_wide_triple(const fp &a, const fp &b, const fp &c, const fp
   fp_mul_wide_rows3<10>(E0, O0, E1, O1, E2, O2, a, b, c, d, e, f);
   return fpw3{fpw_join(E0, O0), fpw_join(E1, O1), fpw_join(E2, O2)};
 }
-// one shift-and-reduce step of fp_redc_wide on (A aligned at word 0 after the shift, B shifted in by two words)
+// one shift-and-reduce step of fp_redc_wide on (A aligned at word 0 after the shift, B shifted in by two words).
+// The two-word shift of B rides on the m * p_odd products (three-operand multiply-add: B[k] = p*m + B[k+2], carry-in = the
+// carry of A[0] += B[1]), exactly like the a*b_i rows of fp_mul — no add-with-carry chain on the ALU pipe per row (round 1
+// spent 12 ALU instructions per row there: 132 of the ~320 non-multiply instructions of a reduction).
 B200_DEV void fp_redc_wide_step(uint32_t *A, uint32_t *B) {
+  uint32_t m;
   ptx_add_cc(A[0], A[0], B[1]);
+  ptx_mul_lo(m, A[0], FP_INV32);  // mul.lo leaves CC.CF alone
 #pragma unroll
-  for (int k = 0; k < 10; k++) ptx_addc_cc(B[k], B[k + 2], 0u);
-  ptx_addc_cc(B[10], 0u, 0u);
-  B[11] = 0;
-  fp_redc_step(A, B);
+  for (int j = 0; j < 10; j += 2) {
+    ptx_madc_lo_cc(B[j], fp_modw(1 + j), m, B[j + 2]);
+    ptx_madc_hi_cc(B[j + 1], fp_modw(1 + j), m, B[j + 3]);
+  }
+  ptx_madc_lo_cc(B[10], fp_modw(11), m, 0u);
+  ptx_madc_hi(B[11], fp_modw(11), m, 0u);  // no carry out (value bound)
+  fp_cmad_row_mod<0>(A, m);
+  ptx_addc(B[11], B[11], 0u);
 }
 B200_DEV fp fp_redc_wide_tail(const uint32_t *ev, const uint32_t *od, const fpw &t) {
   fp r;
