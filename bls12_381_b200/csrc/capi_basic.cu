@@ -136,6 +136,44 @@ __global__ void __launch_bounds__(128) k_mul_batch_warp(const char *p, const uin
   if (lane == 0) proj_store<F>(out + PB * item, acc);
 }
 
+// The same schedule with SEVERAL items per warp: item g of a warp is worked on by the six lanes 6g .. 6g+5 (grp_double / grp_add
+// of curve_warp.cuh), `gpw` = 1..5 items per warp.  A warp-wide field multiplication costs the same issue slots whether 6 or 30
+// lanes are active, and one warp per scheduler (SMSP) already runs at the latency of its dependent chain, so the best shape for
+// a small batch is the SMALLEST gpw that leaves at most one warp per SMSP (config 1: 1024 items -> 2 per warp = 512 warps on
+// 592 SMSPs instead of 1024 warps, two per SMSP).  The addition is executed when ANY item of the warp has its bit set and
+// selected per item.
+template <class F>
+__global__ void __launch_bounds__(32) k_mul_batch_grp(const char *p, const uint32_t *s, char *out, size_t n, int gpw) {
+  const int lane = threadIdx.x & 31;
+  int grp = lane / 6;
+  const int sub = lane - 6 * grp;
+  const size_t item = (size_t)blockIdx.x * gpw + grp;
+  const bool live = grp < gpw && item < n;
+  constexpr size_t PB = 3 * field_traits<F>::bytes;
+  uint32_t by[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) by[k] = 0;
+  proj<F> base = proj_identity<F>(), acc = proj_identity<F>();
+  if (live) {
+    const uint4 *sp = reinterpret_cast<const uint4 *>(s + 8 * item);
+    uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
+    by[0] = lo.x; by[1] = lo.y; by[2] = lo.z; by[3] = lo.w;
+    by[4] = hi.x; by[5] = hi.y; by[6] = hi.z; by[7] = hi.w;
+    base = proj_load<F>(p + PB * item);
+  }
+  const int gbase = 6 * grp;
+#pragma unroll 1
+  for (int bit = 254; bit >= 0; bit--) {
+    acc = grp_double(acc, sub, gbase);
+    const bool mine = (by[bit >> 5] >> (bit & 31)) & 1;
+    if (__any_sync(0xffffffffu, mine)) {
+      proj<F> t = grp_add(acc, base, sub, gbase);
+      acc = proj_select(acc, t, mine);
+    }
+  }
+  if (live && sub == 0) proj_store<F>(out + PB * item, acc);
+}
+
 // batch_normalize (src/g1.rs:806-839): Montgomery's trick per thread over a strided subsequence
 // i = t, t+T, t+2T, ... (coalesced across the warp).  One inversion per thread.  The prefix products
 // are parked in out.x exactly like the reference parks them in q.x.
@@ -254,8 +292,22 @@ inline unsigned nblk(size_t n, unsigned b) { return (unsigned)((n + b - 1) / b);
 template <class F>
 int mul_batch_dev(b200_ctx *ctx, const void *p, const void *s, size_t n, void *out) {
   if (n == 0) return B200_OK;
-  if (n <= 6000) {  // latency regime: one warp per item (crossover with the thread-per-item kernel ~ 4-5 waves)
+  // latency regime: several lanes per item.  tune_mul_groups: -1 = thread per item always, 0 = auto, 1..5 = items per warp of the
+  // group kernel, 6 = round 1's one-warp-per-item kernel
+  const int mg = ctx->tune_mul_groups;
+  if (mg == 6) {
     B200_LAUNCH(ctx, k_mul_batch_warp<F>, nblk(n * 32, 128), 128, 0, (const char *)p, (const uint32_t *)s, (char *)out, n);
+    return B200_OK;
+  }
+  if (mg >= 1 || (mg == 0 && n <= (size_t)ctx->tune_mul_groups_max_n)) {
+    int gpw = mg;
+    if (gpw < 1) {  // the smallest count that leaves at most one warp per scheduler; beyond that, full warps
+      const size_t slots = 4u * (size_t)ctx->sm_count;
+      gpw = (int)((n + slots - 1) / slots);
+      if (gpw < 1) gpw = 1;
+    }
+    if (gpw > 5) gpw = 5;
+    B200_LAUNCH(ctx, k_mul_batch_grp<F>, nblk(n, gpw), 32, 0, (const char *)p, (const uint32_t *)s, (char *)out, n, gpw);
     return B200_OK;
   }
   // small batches: 32-thread blocks so the work spreads over more SMs
@@ -455,6 +507,15 @@ int b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int value) {
   } else if (!strcmp(key, "coop_warps")) {
     if (value < 1 || value > 12) return B200_EINVAL;
     ctx->tune_coop_warps = value;
+  } else if (!strcmp(key, "mul_groups")) {
+    if (value < -1 || value > 6) return B200_EINVAL;
+    ctx->tune_mul_groups = value;
+  } else if (!strcmp(key, "mul_groups_max_n")) {
+    if (value < 0) return B200_EINVAL;
+    ctx->tune_mul_groups_max_n = value;
+  } else if (!strcmp(key, "stagger_ns")) {
+    if (value < 0 || value > 1000000) return B200_EINVAL;
+    ctx->tune_stagger_ns = value;
   } else if (!strcmp(key, "pairing_chunks")) {
     if (value < 1 || value > 64) return B200_EINVAL;
     ctx->tune_pairing_chunks = value;

@@ -78,6 +78,13 @@ struct b200_ctx {
   static constexpr size_t COOP_MAX_PAIRS = 28672;
   bool coop_for(size_t n) const { return tune_pairing_variant == 7 || (tune_pairing_variant == 0 && n <= COOP_MAX_PAIRS); }
   bool coop_products() const { return tune_pairing_variant != 4; }
+  // scalar-multiplication batches (config 1): -1 thread per item, 0 auto (group kernel up to tune_mul_groups_max_n items, items
+  // per warp = ceil(n / (4 * SMs)) clipped to 1..5), 1..5 forced items per warp, 6 = round 1's one warp per item
+  int tune_mul_groups = 0;
+  int tune_mul_groups_max_n = 16384;
+  // start-up stagger of the warps that share a scheduler in the lane-cooperative pairing kernels (nanoseconds per slot, 0 = off):
+  // warps that start together run the same straight-line code in step and reach the multiplier together (convoy)
+  int tune_stagger_ns = 0;
   int tune_coop_warps = 12;          // warps per block (one block per SM) of the lane-cooperative pairing kernels, 1..16
   int tune_coop_split = 1;           // 1: Miller loop and final exponentiation of a pairing batch as two launches of the kernel
   bool coop_attr_done[7] = {};       // cudaFuncSetAttribute(max dynamic shared memory) done on this device, per kernel build

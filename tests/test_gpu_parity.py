@@ -122,6 +122,32 @@ def test_mul_batch_config1(eng, orc, k, n):
     assert eq(got, exp)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [1, 2])
+@pytest.mark.parametrize("groups", [-1, 1, 2, 3, 5, 6])
+def test_mul_batch_items_per_warp(eng, orc, k, groups):
+    """every shape of the scalar-multiplication batch (tuning key mul_groups: thread per item, 1..5 items per warp of the
+    six-lane group kernel, one warp per item) gives the reference's raw (x, y, z) limbs — ragged last warp, zero / one / q-1
+    scalars, an identity point, items of one warp with different scalar bits"""
+    rng = np.random.default_rng(470 + 10 * k + groups)
+    G = orc.G1 if k == 1 else orc.G2
+    n = 43 if k == 1 else 17
+    pr, _, _ = util.rand_points(orc, k, rng, n)
+    p = util.randomize_z(orc, k, rng, pr)
+    s = util.rand_scalars(rng, n)
+    s[0] = 0
+    s[1] = util.scalar_bytes(1)
+    s[2] = util.scalar_bytes(pyref.Q - 1)
+    p[3] = G.identity()
+    s[5] = 0
+    eng.set_tuning("mul_groups", groups)
+    try:
+        got = eng.mul_batch(k, p, s)
+    finally:
+        eng.set_tuning("mul_groups", 0)
+    assert eq(got, G.mul(p, s, threads=8))
+
+
 # ----------------------------------------------------------------------------- MSM
 def _msm_case(eng, orc, k, xy, inf, s, cs=(0,)):
     G = orc.G1 if k == 1 else orc.G2

@@ -64,6 +64,23 @@ def test_mul_batch_config1(eng, orc, k, n):
     GP.test_mul_batch_config1(eng, orc, k, n)        # small n: the warp-per-item kernel (shuffles on the fiber scheduler)
 
 
+def test_mul_batch_three_items_per_warp(eng, orc):
+    """the six-lane group kernel with several items per warp (config 1 runs two per warp on the GPU): 7 items, 3 per warp"""
+    import tests.util as util
+    rng = np.random.default_rng(4711)
+    pr, _, _ = util.rand_points(orc, 1, rng, 7)
+    p = util.randomize_z(orc, 1, rng, pr)
+    s = util.rand_scalars(rng, 7)
+    s[0] = 0
+    p[4] = orc.G1.identity()
+    eng.set_tuning("mul_groups", 3)
+    try:
+        got = eng.mul_batch(1, p, s)
+    finally:
+        eng.set_tuning("mul_groups", 0)
+    assert np.array_equal(got, orc.G1.mul(p, s, threads=4))
+
+
 def test_pairing_and_gt_kat(eng, orc):
     GP.test_gt_generator_kat_on_gpu(eng, orc)
 
