@@ -44,7 +44,7 @@ DEFAULT_LOG2N = {"g1_mul": 10, "g1_msm": 20, "g2_msm": 20, "pairing": 16}
 IMAD_PER_FPM = 300
 UNIT = {"g1_mul": "G1 scalar-muls/s", "g1_msm": "G1 MSM point-scalar-muls/s", "g2_msm": "G2 MSM point-scalar-muls/s",
         "pairing": "pairings/s"}
-DOMINANT = {"g1_mul": "k_mul_batch_warp", "g1_msm": "k_msm_accumulate", "g2_msm": "k_msm_accumulate",
+DOMINANT = {"g1_mul": "k_mul_batch_grp", "g1_msm": "k_msm_accumulate", "g2_msm": "k_msm_accumulate",
             "pairing": "k_coop_pairing"}
 
 
@@ -419,8 +419,12 @@ class Bench:
                 h2d = sum(x.numel() * x.element_size() for x in hp) * world
                 d2h = n_local * 576 * world
 
+                hgt = torch.empty((n_local, 72), dtype=torch.int64).pin_memory()       # caller-owned pinned result buffer
+                hgt_np = hgt.numpy().view(np.uint64)
+
                 def step_host():
-                    eng.pairing_batch(hp[0].numpy().view(np.uint64), hp[1].numpy(), hp[2].numpy().view(np.uint64), hp[3].numpy())
+                    eng.pairing_batch(hp[0].numpy().view(np.uint64), hp[1].numpy(), hp[2].numpy().view(np.uint64), hp[3].numpy(),
+                                      out=hgt_np)
             elif wl == "g1_mul":
                 hpr, hsc = pin(pr), pin(sc)
                 h2d, d2h = (hpr.numel() * 8 + hsc.numel()) * world, hpr.numel() * 8 * world
@@ -479,6 +483,8 @@ class Bench:
                     base = "k_msm_accumulate"           # G1 / G2-register / G2-shared-memory variants of the bucket kernel
                 per_kernel.setdefault(base, []).append(ms)
             dom = DOMINANT[wl]
+            if wl == "g1_mul" and dom not in per_kernel:      # forced shapes (--tune mul_groups=6 / -1)
+                dom = next((c for c in ("k_mul_batch_warp", "k_mul_batch") if c in per_kernel), dom)
             chunked_v4 = False
             if wl == "pairing" and dom not in per_kernel:
                 # one-thread-per-pairing kernels (what the default picks above 28 672 pairs): Miller loop and final exponentiation
@@ -504,9 +510,11 @@ class Bench:
                     fpm = fpm_exec = 5100.0 * n_local
                     alg_bytes = (144 * 2 + 32) * n_local
                 elif dom == "k_coop_pairing":
-                    # the six-lane kernel: Miller loop + final exponentiation (the model's 16 020 FpM per pairing)
+                    # the six-lane kernels: G2 line coefficients (k_g2_prepare) + Miller loop + final exponentiation together are
+                    # the model's 16 020 FpM per pairing, so the three launches are timed together
                     fpm = fpm_exec = 16020.0 * n_local
                     alg_bytes = (96 + 192 + 576) * n_local
+                    avg_ms += sum(per_kernel.get("k_g2_prepare", [])) / steps
                 else:
                     fpm = fpm_exec = 16020.0 * n_local                      # k_miller_loop + k_final_exp together (whole step)
                     alg_bytes = (96 + 192 + 576) * n_local
@@ -538,6 +546,11 @@ class Bench:
                         "hbm": {"achieved_gbs": alg_bytes / (avg_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                                 "frac": alg_bytes / (avg_ms * 1e-3) / 1e9 / hbm_peak, "of": hbm_of},
                         "kernel_ms": {kname: sum(v) / steps for kname, v in per_kernel.items()}}
+                if wl == "g2_msm":
+                    roof["frac_note"] = ("the SURVEY 8d model prices an Fp2 multiplication at 3 FpM = 900 multiply-adds (the "
+                                         "reference's Karatsuba); the kernel's lazy-reduction Fp2 multiply executes 744, so the "
+                                         "model fraction can exceed 1 — executed_frac counts 10 Fp2 products x 744")
+                    roof["executed_frac"] = 10 * 744.0 * n_eff * nwin_local / (avg_ms * 1e-3) / peak
                 roof["model_frac_whole_step"] = (model_fpm(wl, log2n) * IMAD_PER_FPM * n / world / (ms_per_step * 1e-3) / peak)
 
         cpu = None

@@ -494,6 +494,9 @@ int b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int value) {
     ctx->tune_g1_glv = value;
   } else if (!strcmp(key, "msm_tail_groups")) {
     ctx->tune_msm_tail_groups = value != 0;
+  } else if (!strcmp(key, "msm_sort")) {
+    if (value < 0 || value > 4096) return B200_EINVAL;   // 0 global atomics, 1 shared-memory sort, >= 2: same with that many scalars per slice (tests)
+    ctx->tune_msm_sort = value;
   } else if (!strcmp(key, "msm_reduce")) {
     if (value < -1 || value > 2) return B200_EINVAL;
     ctx->tune_msm_reduce = value;

@@ -47,6 +47,10 @@ struct b200_ctx {
 #else
   int tune_msm_reduce = -1;
 #endif
+  // counting sort of the window digits: 1 = per-block histograms and cursors in shared memory (no global atomics; windows of
+  // c <= 16 bits), 0 = round 1's global-atomic count / scatter
+  int tune_msm_sort = 1;
+  bool msm_sort_attr_done = false;
   int tune_msm_tail_groups = 1;  // 2-3 local windows (window shards of a multi-GPU MSM): one window per group (1) or one group (0)
   int tune_g1_prefetch = 1;    // G1 bucket kernel: cp.async double-buffered prefetch of the next point (1) or plain loads (0)
   int tune_pairing_chunks = 4; // independent Miller+final-exp chunks of a pairing batch kept in flight on 2 streams
@@ -71,17 +75,16 @@ struct b200_ctx {
   // Miller loop / final exponentiation kernels: 4 = pairing_v4.cu, one thread per pairing (round 1).  The dual- / triple-
   // stream Fp2-multiply builds (v5 / v6) measured slower on B200 (63.5 / 67.4 vs 59.3 ms at 2^16 pairs) and were removed.
   // 7 = pairing_coop.cu: six lanes per pairing, Fp12 distributed over the lanes (round 2).
-  // 0 = automatic (default): batched pairings / Miller loops / final exponentiations of at most COOP_MAX_PAIRS items use the
-  // six-lane kernels (one wave needs 8 880 pairs instead of 37 888: 9.1 vs 22.0 ms at 8 192 pairs, 16.0 vs 22.7 ms at 16 384),
-  // larger batches the one-thread-per-pairing kernels (59.3 vs 61.8 ms at 65 536); products (shared squaring) always 7.
+  // 0 = automatic (default) = the six-lane kernels at every batch size: one wave needs 8 880 pairs instead of 37 888 (9.1 vs
+  // 22.0 ms at 8 192 pairs, 16.0 vs 22.7 ms at 16 384), and since the Montgomery reduction of the lazy dot products lost its
+  // shift chains they also win on large batches (58.0 vs 60.8 ms at 65 536; before: 61.8 vs 59.3).  4 stays selectable.
   int tune_pairing_variant = 0;
-  static constexpr size_t COOP_MAX_PAIRS = 28672;
-  bool coop_for(size_t n) const { return tune_pairing_variant == 7 || (tune_pairing_variant == 0 && n <= COOP_MAX_PAIRS); }
+  bool coop_for(size_t) const { return tune_pairing_variant != 4; }
   bool coop_products() const { return tune_pairing_variant != 4; }
   // scalar-multiplication batches (config 1): -1 thread per item, 0 auto (group kernel up to tune_mul_groups_max_n items, items
   // per warp = ceil(n / (4 * SMs)) clipped to 1..5), 1..5 forced items per warp, 6 = round 1's one warp per item
   int tune_mul_groups = 0;
-  int tune_mul_groups_max_n = 16384;
+  int tune_mul_groups_max_n = 9000;   // measured crossover with the thread-per-item kernel (G1): 8192 -> 5.05 vs 5.64 ms, 16384 -> 7.67 vs 5.63 ms
   // start-up stagger of the warps that share a scheduler in the lane-cooperative pairing kernels (nanoseconds per slot, 0 = off):
   // warps that start together run the same straight-line code in step and reach the multiplier together (convoy)
   int tune_stagger_ns = 0;

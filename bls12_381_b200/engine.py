@@ -337,9 +337,14 @@ class Engine:
         self._ck(self.lib.b200_final_exponentiation_batch(self.h, _hp(f), f.shape[0], _hp(out)), "final_exp")
         return out
 
-    def pairing_batch(self, pxy, pinf, qxy, qinf):
+    def pairing_batch(self, pxy, pinf, qxy, qinf, out=None):
+        """out: optional caller-owned (n, 72) uint64 result buffer (a pinned one makes the 576-byte-per-pair read-back a
+        direct DMA instead of a staged copy into freshly faulted pageable memory)"""
         pxy, pinf, qxy, qinf = self._pairs(pxy, pinf, qxy, qinf)
-        out = np.empty((pxy.shape[0], 72), np.uint64)
+        if out is None:
+            out = np.empty((pxy.shape[0], 72), np.uint64)
+        elif out.shape != (pxy.shape[0], 72) or out.dtype != np.uint64 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous (n, 72) uint64 array")
         self._ck(self.lib.b200_pairing_batch(self.h, _hp(pxy), _hp(pinf), _hp(qxy), _hp(qinf), pxy.shape[0], _hp(out)),
                  "pairing_batch")
         return out
