@@ -494,9 +494,6 @@ int b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int value) {
     ctx->tune_g1_glv = value;
   } else if (!strcmp(key, "msm_tail_groups")) {
     ctx->tune_msm_tail_groups = value != 0;
-  } else if (!strcmp(key, "msm_sort")) {
-    if (value < 0 || value > 4096) return B200_EINVAL;   // 0 global atomics, 1 shared-memory sort, >= 2: same with that many scalars per slice (tests)
-    ctx->tune_msm_sort = value;
   } else if (!strcmp(key, "msm_reduce")) {
     if (value < -1 || value > 2) return B200_EINVAL;
     ctx->tune_msm_reduce = value;
@@ -516,9 +513,6 @@ int b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int value) {
   } else if (!strcmp(key, "mul_groups_max_n")) {
     if (value < 0) return B200_EINVAL;
     ctx->tune_mul_groups_max_n = value;
-  } else if (!strcmp(key, "stagger_ns")) {
-    if (value < 0 || value > 1000000) return B200_EINVAL;
-    ctx->tune_stagger_ns = value;
   } else if (!strcmp(key, "pairing_chunks")) {
     if (value < 1 || value > 64) return B200_EINVAL;
     ctx->tune_pairing_chunks = value;

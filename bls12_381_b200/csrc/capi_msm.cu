@@ -161,56 +161,11 @@ __global__ void __launch_bounds__(256) k_msm_scatter(msm_plan pl, const uint32_t
   });
 }
 
-// ---- counting sort through SHARED-MEMORY histograms (round 2; windows of c <= 16 bits: 2^(c-1) counters = at most 128 KB).
-// The kernels above pay one GLOBAL atomic per (scalar, window) twice (16.7 M at 2^20 x 16 windows: 1.6 + 0.4 ms, and the first
-// window group's share sits in front of the first bucket kernel).  Here a block owns one (window, slice of the scalars):
-//   k_msm_count_sm    histogram of its slice in shared memory (shared-memory atomics), written out as its row of `bh`
-//   k_msm_colsum      per bucket: total over the slices -> hist; bh[slice][bucket] := entries of the earlier slices
-//   k_msm_scan        (as before) exclusive scan of hist over the buckets -> offsets
-//   k_msm_scatter_sm  cursors = offsets + bh row in shared memory; the slice is walked again and every entry is placed with a
-//                     shared-memory atomic — no global atomics anywhere, and the rows make the scatter independent per block.
-// bh layout: [window of the group][slice][bucket].
-constexpr int SORT_THREADS = 512;
-template <bool SCATTER>
-__global__ void __launch_bounds__(SORT_THREADS) k_msm_sort_sm(msm_plan pg, const uint32_t *scalars, const uint8_t *inf, size_t n,
-                                                            int slices, uint32_t *bh, const uint32_t *offsets, size_t sstride,
-                                                            uint32_t *sorted, uint32_t *bad) {
-  B200_DYN_SMEM(uint32_t, sh);
-  const int j = blockIdx.y, sl = blockIdx.x, nb = pg.nbuckets;
-  uint32_t *row = bh + ((size_t)j * slices + sl) * nb;
-  for (int b = threadIdx.x; b < nb; b += SORT_THREADS) sh[b] = SCATTER ? offsets[(size_t)j * nb + b] + row[b] : 0u;
-  __syncthreads();
-  const size_t lo = n * (size_t)sl / slices, hi = n * (size_t)(sl + 1) / slices;
-  for (size_t i = lo + threadIdx.x; i < hi; i += SORT_THREADS) {
-    if (inf && inf[i]) continue;
-    uint32_t s[8];
-    load_scalar(s, scalars, i);
-    if (!SCATTER && bad != nullptr && j == 0 && scalar_ge_q(s)) *bad = 1u;
-    for_each_digit(pg, s, [&](int jj, uint32_t b, uint32_t flags) {
-      if (jj != j) return;
-      uint32_t pos = atomicAdd(&sh[b], 1u);
-      if (SCATTER) sorted[(size_t)j * sstride + pos] = (uint32_t)i | flags;
-    });
-  }
-  if (!SCATTER) {
-    __syncthreads();
-    for (int b = threadIdx.x; b < nb; b += SORT_THREADS) row[b] = sh[b];
-  }
-}
-// one thread per (window of the group, bucket): hist = column sum over the slices, bh := exclusive prefix down the column
-__global__ void __launch_bounds__(256) k_msm_colsum(int nbuckets, int slices, uint32_t *bh, uint32_t *hist) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
-  if (b >= nbuckets) return;
-  uint32_t *col = bh + (size_t)j * slices * nbuckets + b;
-  uint32_t run = 0;
-  for (int sl = 0; sl < slices; sl++) {
-    uint32_t v = col[(size_t)sl * nbuckets];
-    col[(size_t)sl * nbuckets] = run;
-    run += v;
-  }
-  hist[(size_t)j * nbuckets + b] = run;
-}
-
+// (Round 2 tried the north-star's staging of this sort: per-block histograms and cursors in SHARED memory — one block per
+// (window, slice of the scalars), 2^15 counters = 128 KB, slice rows + column sums instead of global atomics (commit 78b2ab7 "MSM:
+// counting sort through per-block shared-memory histograms").  Measured on B200, isolated kernel times (ncu, 2^20 scalars, 16
+// windows): global atomics count 0.21 + scan 0.25 + scatter 0.29 = 0.76 ms per MSM — the L2 retires ~110 G atomics/s — against
+// 0.54 + 0.61 (column sums) + 0.25 + 0.60 = 2.0 ms; whole step 9.37 vs 8.50 ms.  Removed; records in profiles/.)
 // ---- bucket scheduling: order (window,bucket) slots by population, largest first, so the 32 lanes of
 // a warp walk buckets of (nearly) equal length (round-1 ncu: 23/32 active lanes with natural order) and
 // the last, partially filled wave holds only the short buckets.  Counting sort on min(count, 1023).
@@ -733,10 +688,6 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
                 arena_pad(total * PB) + arena_pad((size_t)pl.nloc * blocks_per_window * PB) + arena_pad(PB) +
                 (pl.glv ? arena_pad(48 * n) : 0) + arena_pad((size_t)max_giants * GIANT_PARTS * PB) + 4096 + 256 +
                 (coop_reduce ? r_bytes : 0);
-  // shared-memory counting sort (tune_msm_sort: 1 = on when the window's counters fit, 0 = global atomics): rows of one group
-  const bool sort_sm = ctx->tune_msm_sort != 0 && (size_t)pl.nbuckets * 4 <= 128 * 1024;
-  const size_t bh_words = sort_sm ? (size_t)(ctx->sm_count > pl.nloc ? ctx->sm_count : pl.nloc) * pl.nbuckets : 0;
-  need += arena_pad(bh_words * 4);
   if (ctx->tune_msm_affine_levels != 0) {  // upper bound of the affine-level scratch (largest group <= all local windows)
     need += 8 * arena_pad(total * 4) + 3 * 256;
     for (int l = 1; l <= 3; l++) need += arena_pad((size_t)pl.nloc * ((sstride >> l) + pl.nbuckets + 8) * 2 * field_traits<F>::bytes);
@@ -758,7 +709,6 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
     for (int l = 0; l < r_levels; l++) r_buf[l] = arena_take<char>(ctx, (size_t)pl.nloc * r_n[l] * PB);
   char *bx = pl.glv ? arena_take<char>(ctx, 48 * n) : nullptr;
   char *gparts = arena_take<char>(ctx, (size_t)max_giants * GIANT_PARTS * PB);
-  uint32_t *bh = sort_sm ? arena_take<uint32_t>(ctx, bh_words) : nullptr;
   uint32_t *bad = arena_take<uint32_t>(ctx, 1);
   ctx->msm_bad_flag = bad;
   B200_CUDA(ctx, cudaMemsetAsync(bad, 0, sizeof(uint32_t), ctx->stream));
@@ -859,31 +809,6 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
     pg.nloc = cnt;
     for (int i = 0; i < cnt; i++) pg.win[i] = pl.win[j_lo + i];
     size_t s0 = (size_t)j_lo * pl.nbuckets;
-    if (sort_sm) {
-      int slices = ctx->sm_count / cnt;          // one block per SM (its counters take up to 128 KB of shared memory)
-      if (slices < 1) slices = 1;
-      const size_t gran = ctx->tune_msm_sort >= 2 ? (size_t)ctx->tune_msm_sort : (size_t)SORT_THREADS;  // (>= 2: test hook, scalars per slice)
-      if ((size_t)slices * gran > n) slices = (int)((n + gran - 1) / gran);
-      const size_t smem = (size_t)pl.nbuckets * 4;
-#ifndef B200_HOST_EMUL
-      if (!ctx->msm_sort_attr_done) {   // up to 128 KB of dynamic shared memory
-        cudaError_t e = cudaFuncSetAttribute(k_msm_sort_sm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_msm_sort_sm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-        if (e != cudaSuccess) return b200::set_err(ctx, e, "cudaFuncSetAttribute(k_msm_sort_sm)");
-        ctx->msm_sort_attr_done = true;
-      }
-#endif
-      dim3 grid((unsigned)slices, (unsigned)cnt);
-      B200_LAUNCH_ON(ctx, st, (k_msm_sort_sm<false>), grid, SORT_THREADS, smem, pg, (const uint32_t *)scalars, (const uint8_t *)inf, n,
-                     slices, bh, (const uint32_t *)nullptr, sstride, (uint32_t *)nullptr,
-                     st == ctx->stream ? bad : (uint32_t *)nullptr);
-      dim3 cgrid(nblk((size_t)pl.nbuckets, 256), (unsigned)cnt);
-      B200_LAUNCH_ON(ctx, st, k_msm_colsum, cgrid, 256, 0, pl.nbuckets, slices, bh, hist + s0);
-      B200_LAUNCH_ON(ctx, st, k_msm_scan, cnt, 1024, 0, pl.nbuckets, hist + s0, offsets + s0);
-      B200_LAUNCH_ON(ctx, st, (k_msm_sort_sm<true>), grid, SORT_THREADS, smem, pg, (const uint32_t *)scalars, (const uint8_t *)inf, n,
-                     slices, bh, offsets + s0, sstride, sorted + (size_t)j_lo * sstride, (uint32_t *)nullptr);
-      return B200_OK;
-    }
     B200_LAUNCH_ON(ctx, st, k_msm_count, nblk(n, 256), 256, 0, pg, (const uint32_t *)scalars, (const uint8_t *)inf, n, hist + s0,
                    st == ctx->stream ? bad : (uint32_t *)nullptr);   // checked once, by the first group (main stream)
     B200_LAUNCH_ON(ctx, st, k_msm_scan, cnt, 1024, 0, pl.nbuckets, hist + s0, offsets + s0);
@@ -894,10 +819,6 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
   {
     int rc0 = sort_group(ctx->stream, pl.nloc - gsz[0], gsz[0]);
     if (rc0 != B200_OK) return rc0;
-    if (sort_sm && ng > 1) {   // the slice rows (bh) are one buffer: the next group's sort (stream2) starts after this one
-      B200_CUDA(ctx, cudaEventRecord(ctx->ev_sync[19], ctx->stream));
-      B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_sync[19], 0));
-    }
   }
   int j_top = pl.nloc - 1, prev_w = -1;
   for (int g = 0; g < ng; g++) {

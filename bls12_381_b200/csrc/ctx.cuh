@@ -47,10 +47,6 @@ struct b200_ctx {
 #else
   int tune_msm_reduce = -1;
 #endif
-  // counting sort of the window digits: 1 = per-block histograms and cursors in shared memory (no global atomics; windows of
-  // c <= 16 bits), 0 = round 1's global-atomic count / scatter
-  int tune_msm_sort = 1;
-  bool msm_sort_attr_done = false;
   int tune_msm_tail_groups = 1;  // 2-3 local windows (window shards of a multi-GPU MSM): one window per group (1) or one group (0)
   int tune_g1_prefetch = 1;    // G1 bucket kernel: cp.async double-buffered prefetch of the next point (1) or plain loads (0)
   int tune_pairing_chunks = 4; // independent Miller+final-exp chunks of a pairing batch kept in flight on 2 streams
@@ -85,9 +81,6 @@ struct b200_ctx {
   // per warp = ceil(n / (4 * SMs)) clipped to 1..5), 1..5 forced items per warp, 6 = round 1's one warp per item
   int tune_mul_groups = 0;
   int tune_mul_groups_max_n = 9000;   // measured crossover with the thread-per-item kernel (G1): 8192 -> 5.05 vs 5.64 ms, 16384 -> 7.67 vs 5.63 ms
-  // start-up stagger of the warps that share a scheduler in the lane-cooperative pairing kernels (nanoseconds per slot, 0 = off):
-  // warps that start together run the same straight-line code in step and reach the multiplier together (convoy)
-  int tune_stagger_ns = 0;
   int tune_coop_warps = 12;          // warps per block (one block per SM) of the lane-cooperative pairing kernels, 1..16
   int tune_coop_split = 1;           // 1: Miller loop and final exponentiation of a pairing batch as two launches of the kernel
   bool coop_attr_done[7] = {};       // cudaFuncSetAttribute(max dynamic shared memory) done on this device, per kernel build

@@ -110,19 +110,6 @@ B200_DEV fp2 co_final_exponentiation(const cgrp &g, const fp2 &f, const uint32_t
 
 constexpr int CO_FLAG_MILLER = 1, CO_FLAG_FINAL_EXP = 2;
 
-// Warps w, w + 4, w + 8 of the block share a scheduler (SMSP).  Launched together they run the same straight-line code in
-// step: all of them want the multiplier at the same time and all of them sit in the add/sub/select glue at the same time
-// (a convoy: the pipe idles during the glue however many warps there are).  A start-up offset of a fraction of one
-// operation puts them out of phase; fair sharing of the pipe then preserves the offset.
-B200_DEV void co_stagger(int stagger_ns, int warp) {
-#ifndef B200_HOST_EMUL
-  if (stagger_ns > 0)
-    for (int s = warp >> 2; s > 0; s--) __nanosleep((unsigned)stagger_ns);
-#else
-  (void)stagger_ns; (void)warp;
-#endif
-}
-
 // Product mode: item i = the product over the `terms` consecutive pairs [i * terms, (i + 1) * terms) — ONE Miller value
 // (and, with final_exp, one Gt) per item.  Groth16 / BLS batch verification: terms = 3..4, n_items = number of proofs;
 // a single large product: n_items = number of term chunks, the partial products are multiplied by k_coop_product.
@@ -185,14 +172,13 @@ __global__ void __launch_bounds__(MAXT, 1) k_coop_product(const char *in, size_t
 // flags & 1: f = Miller loop of (P_i, prepared Q_i) else f = in[i];  flags & 2: f = final_exponentiation(f).
 // One warp = 5 pairs; grid-stride over groups of 5.
 template <int MAXT, int FLAGS>
-__global__ void __launch_bounds__(MAXT, 1) k_coop_pairing(int stagger_ns, const char *pxy, const uint8_t *pinf, const char *coeffs,
+__global__ void __launch_bounds__(MAXT, 1) k_coop_pairing(int, const char *pxy, const uint8_t *pinf, const char *coeffs,
                                                         const uint8_t *qinf, const char *in, size_t n, char *out,
                                                         const uint32_t *pow2) {
   B200_DYN_SMEM(uint32_t, smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const int grp = lane / CO_LANES;
   if (grp >= CO_GROUPS) return;   // lanes 30, 31: no group
-  co_stagger(stagger_ns, warp);
   cgrp g;
   g.k = lane - CO_LANES * grp;
   g.mask = 0x3fu << (CO_LANES * grp);
@@ -250,7 +236,7 @@ int b200_pair_coop_launch(b200_ctx *ctx, cudaStream_t strm, int flags, const voi
 #define CO_LAUNCH(MAXT, FL)                                                                                                  \
   do {                                                                                                                       \
     CO_SET_ATTR(MAXT, FL)                                                                                                    \
-    B200_LAUNCH_ON(ctx, strm, (k_coop_pairing<MAXT, FL>), grid, 32 * warps, smem, ctx->tune_stagger_ns, (const char *)p,                    \
+    B200_LAUNCH_ON(ctx, strm, (k_coop_pairing<MAXT, FL>), grid, 32 * warps, smem, flags, (const char *)p,                    \
                    (const uint8_t *)pi, (const char *)coeffs, (const uint8_t *)qi, (const char *)in, n, (char *)out,        \
                    (const uint32_t *)ctx->inv_pow2);                                                                         \
   } while (0)

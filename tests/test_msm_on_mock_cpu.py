@@ -142,27 +142,3 @@ def test_cooperative_bucket_reduction(eng, orc, data):
     finally:
         eng.set_tuning("msm_reduce", 0)
 
-
-def test_global_atomic_counting_sort_still_works(eng, orc, data):
-    """msm_sort = 0: round 1's k_msm_count / k_msm_scatter (global atomics) — the path wider windows (c > 16) still take; the
-    default (per-block histograms and cursors in shared memory, k_msm_sort_sm / k_msm_colsum) is what every other test here runs"""
-    xy, inf, s = data[1]
-    eng.set_tuning("msm_sort", 0)
-    try:
-        GP._msm_case(eng, orc, 1, *_edge_set(orc, 1, xy, inf, s, 40), cs=(0, 6))
-        eng.set_tuning("g1_glv", 1)
-        GP._msm_case(eng, orc, 1, xy[:21], inf[:21], s[:21], cs=(5,))
-    finally:
-        eng.set_tuning("g1_glv", 0)
-        eng.set_tuning("msm_sort", 1)
-
-
-def test_shared_memory_sort_with_many_slices(eng, orc, data):
-    """msm_sort = 3: three scalars per slice, so the slice rows, their column sums and the per-slice cursors of
-    k_msm_sort_sm / k_msm_colsum are exercised with a dozen blocks per window (on hardware a slice is >= 512 scalars)"""
-    xy, inf, s = data[1]
-    eng.set_tuning("msm_sort", 3)
-    try:
-        GP._msm_case(eng, orc, 1, *_edge_set(orc, 1, xy, inf, s, 40), cs=(0, 6))
-    finally:
-        eng.set_tuning("msm_sort", 1)

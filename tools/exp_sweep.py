@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Round-2 tuning sweeps on one GPU (not a bench line: device-timed kernels, per-kernel CUDA-event records of the library).
 
-    python tools/exp_sweep.py pairing  [--log2n 16]     pairing batch: variant x coop_warps x stagger_ns
+    python tools/exp_sweep.py pairing  [--log2n 16]     pairing batch: variant x coop_warps
     python tools/exp_sweep.py mul                        scalar-multiplication batch: n x mul_groups
 Prints one JSON object per measurement."""
 import argparse
@@ -50,7 +50,6 @@ def main():
     ap.add_argument("what", choices=["pairing", "mul"])
     ap.add_argument("--log2n", type=int, default=16)
     ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--stagger", default="0,250,500,1000,2000,4000")
     ap.add_argument("--warps", default="12")
     ap.add_argument("--variants", default="7,4")
     a = ap.parse_args()
@@ -81,15 +80,13 @@ def main():
                 for w in ([int(x) for x in a.warps.split(",")] if var == 7 else [0]):
                     if var == 7:
                         eng.set_tuning("coop_warps", w)
-                    for st in [int(x) for x in a.stagger.split(",")]:
-                        eng.set_tuning("stagger_ns", st)
-                        ms = timed(torch, stream, fn, a.reps, flush)
-                        km = kernel_ms(eng, fn, stream)
-                        h = int(out.sum().item()) & 0xffffffff
-                        if ref is None:
-                            ref = h
-                        print(json.dumps({"what": "pairing", "n": n, "variant": var, "coop_warps": w, "stagger_ns": st,
-                                          "ms": [round(x, 3) for x in ms], "kernels": km, "same_result": h == ref}), flush=True)
+                    ms = timed(torch, stream, fn, a.reps, flush)
+                    km = kernel_ms(eng, fn, stream)
+                    h = int(out.sum().item()) & 0xffffffff
+                    if ref is None:
+                        ref = h
+                    print(json.dumps({"what": "pairing", "n": n, "variant": var, "coop_warps": w,
+                                      "ms": [round(x, 3) for x in ms], "kernels": km, "same_result": h == ref}), flush=True)
         else:
             from bls12_381_b200 import constants_host as ch
             for k in (1, 2):

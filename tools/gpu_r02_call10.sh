@@ -4,7 +4,7 @@
 set -u
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q -x -p no:cacheprovider 2>&1 | tail -6 > gpurun_out/r02_c10_pytest.txt
-timeout 300 python tools/exp_sweep.py pairing --stagger 0,250,500,1000,2000,4000,8000 --warps 12,8 > gpurun_out/r02_c10_pairing.jsonl 2> gpurun_out/r02_c10_pairing.err
+timeout 300 python tools/exp_sweep.py pairing --warps 12,8 > gpurun_out/r02_c10_pairing.jsonl 2> gpurun_out/r02_c10_pairing.err
 timeout 300 python tools/exp_sweep.py mul > gpurun_out/r02_c10_mul.jsonl 2> gpurun_out/r02_c10_mul.err
 timeout 300 python bench.py --workload g2_msm --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r02_c10_g2_msm.json 2> gpurun_out/r02_c10_g2.err
 cat gpurun_out/r02_c10_pytest.txt
