@@ -178,11 +178,27 @@ B200_NOINL fp2 co_mul_sparse(cgrp g, fp2 x, const uint32_t *pc0, const uint32_t 
   return z;
 }
 
+// p - a as a plain 384-bit subtraction: the negative of a canonical a, except that 0 maps to p (not canonical).  Safe as the
+// SECOND operand of fp_add with a canonical first operand: a' + p - p = a'.  Never add two of these to each other.
+B200_DEV fp fp_neg_lazy(const fp &a) {
+  fp r;
+  ptx_sub_cc(r.v[0], fp_modw(0), a.v[0]);
+#pragma unroll
+  for (int i = 1; i < 11; i++) ptx_subc_cc(r.v[i], fp_modw(i), a.v[i]);
+  ptx_subc(r.v[11], fp_modw(11), a.v[11]);
+  return r;
+}
+
 // cyclotomic_square (src/pairings.rs:66-113).  The three fp4_square calls work on the coefficient pairs
 // (x0, x3), (x1, x4), (x2, x5); lanes q and q + 3 share pair q: each squares its own coefficient (two Fp products) and
 // takes one half of (a + b)^2 — three Fp multiplications per lane, the 18 of the reference spread evenly.
-B200_NOINL fp2 co_cyclotomic_sqr(cgrp g, fp2 x) {
-  constexpr int S_T = 6, S_H = 12;
+// Every lane publishes its square t AND p - t, so that the two kinds of output coefficient
+//   c0 = a^2 + xi b^2 = (t0.re + t1.re - t1.im,  t0.im + t1.re + t1.im)          (even lanes)
+//   c1 = (a+b)^2 - a^2 - b^2 = (H.re - t0.re - t1.re,  H.im - t0.im - t1.im)       (odd lanes)
+// are the SAME instruction sequence — three-term sums over lane-specific pointers — instead of two divergent branches that a
+// warp executes one after the other (round 2, first version: 10 modular additions per lane and squaring, now 4).
+B200_DEV fp2 co_cyclotomic_sqr_body(const cgrp &g, const fp2 &x) {
+  constexpr int S_T = 6, S_H = 12, S_NT = 15;
   const int k = g.k;
   const uint32_t *bd = g.bd;
   co_put(g, CS_F + k, x);
@@ -190,30 +206,43 @@ B200_NOINL fp2 co_cyclotomic_sqr(cgrp g, fp2 x) {
   const bool alane = k < 3;
   fp2 y = co_ld2(bd + CO_SLOT * (CS_F + co_mod6(k + 3)));
   fp2 s = fp2_add(x, y);
-  fp2 own{fp_mul_c(fp_add(x.c0, x.c1), fp_sub(x.c0, x.c1)), fp_mul_c(fp_dbl(x.c0), x.c1)};
-  fp hu = alane ? fp_add(s.c0, s.c1) : fp_dbl(s.c0);
-  fp hv = alane ? fp_sub(s.c0, s.c1) : s.c1;
+  // sums that only feed a multiplication stay unreduced (< 2p; the product of the operand bounds stays far below 2^384 / p = 9.8,
+  // so the one conditional subtraction of fp_mul still lands in [0, p))
+  fp2 own{fp_mul_c(fp_add_nr(x.c0, x.c1), fp_sub(x.c0, x.c1)), fp_mul_c(fp_add_nr(x.c0, x.c0), x.c1)};
+  fp hu = fp_add_nr(s.c0, fp_select(s.c0, s.c1, alane));   // a-lane: s0 + s1, b-lane: 2 s0
+  fp hv = fp_select(s.c1, fp_sub(s.c0, s.c1), alane);      // a-lane: s0 - s1, b-lane: s1
   fp h = fp_mul_c(hu, hv);  // a-lane: re (a+b)^2, b-lane: im (a+b)^2
   co_put(g, S_T + k, own);
+  co_put(g, S_NT + k, fp2{fp_neg_lazy(own.c0), fp_neg_lazy(own.c1)});
   co_put_half(g, S_H + (alane ? k : k - 3), alane ? 0 : 1, h);
   co_sync(g);
   // which pair feeds lane k, and how (z-names of the reference: x0=z0, x3=z1, x1=z2, x4=z3, x2=z4, x5=z5):
   //   x0 <- 3 c0(0) - 2 x0, x3 <- 3 c1(0) + 2 x3, x2 <- 3 c0(1) - 2 x2, x5 <- 3 c1(1) + 2 x5, x1 <- 3 xi c1(2) + 2 x1, x4 <- 3 c0(2) - 2 x4
   const int q = k == 0 || k == 3 ? 0 : (k == 2 || k == 5 ? 1 : 2);
   const bool use_c0 = k == 0 || k == 2 || k == 4;
-  fp2 t0 = co_ld2(bd + CO_SLOT * (S_T + q)), t1 = co_ld2(bd + CO_SLOT * (S_T + q + 3));
-  fp2 c;
-  if (use_c0) {
-    c = fp2_add(fp2_mul_by_nonresidue(t1), t0);                       // xi b^2 + a^2
-  } else {
-    c = fp2_sub(fp2_sub(co_ld2(bd + CO_SLOT * (S_H + q)), t0), t1);   // (a+b)^2 - a^2 - b^2
-    if (k == 1) c = fp2_mul_by_nonresidue(c);
-  }
-  fp2 d = use_c0 ? fp2_sub(c, x) : fp2_add(c, x);
+  const uint32_t *T0 = bd + CO_SLOT * (S_T + q), *T1 = bd + CO_SLOT * (S_T + q + 3);
+  const uint32_t *N0 = bd + CO_SLOT * (S_NT + q), *N1 = bd + CO_SLOT * (S_NT + q + 3), *H = bd + CO_SLOT * (S_H + q);
+  // canonical operands first, at most one `p - t` per addition (fp_neg_lazy)
+  const uint32_t *r0 = use_c0 ? T0 : H, *r1 = use_c0 ? T1 : N0, *r2 = use_c0 ? N1 + 12 : N1;
+  const uint32_t *i0 = use_c0 ? T0 + 12 : H + 12, *i1 = use_c0 ? T1 : N0 + 12, *i2 = use_c0 ? T1 + 12 : N1 + 12;
+  fp2 c{fp_add(fp_add(co_ld(r0), co_ld(r1)), co_ld(r2)), fp_add(fp_add(co_ld(i0), co_ld(i1)), co_ld(i2))};
+  if (k == 1) c = fp2_mul_by_nonresidue(c);
+  // d = c - x (even lanes) / c + x (odd lanes), r = 2 d + c
+  fp2 xt{fp_select(x.c0, fp_neg_lazy(x.c0), use_c0), fp_select(x.c1, fp_neg_lazy(x.c1), use_c0)};
+  fp2 d = fp2_add(c, xt);
   fp2 r = fp2_add(fp2_dbl(d), c);
   co_sync(g);
   return r;
 }
+// n >= 1 squarings in a row: the loop lives INSIDE the called function (one copy of the body, the accumulator stays in its
+// registers) — called once per squaring, the argument / result moves and the caller's spills around the call were 280 of the
+// 2 600 instructions of a squaring
+B200_NOINL fp2 co_cyclotomic_sqr_n(cgrp g, fp2 x, int n) {
+#pragma unroll 1
+  for (; n > 0; n--) x = co_cyclotomic_sqr_body(g, x);
+  return x;
+}
+B200_DEV fp2 co_cyclotomic_sqr(const cgrp &g, const fp2 &x) { return co_cyclotomic_sqr_n(g, x, 1); }
 
 // frobenius_map^n, n = 1..3 (src/fp12.rs:145-171 applied n times): coefficient-wise conj^n(x_k) * xi^(k (p^n - 1)/6)
 B200_NOINL fp2 co_frobenius(cgrp g, fp2 x, int n) {

@@ -47,7 +47,11 @@ struct b200_ctx {
 #else
   int tune_msm_reduce = -1;
 #endif
-  int tune_msm_tail_groups = 1;  // 2-3 local windows (window shards of a multi-GPU MSM): one window per group (1) or one group (0)
+  // 2-3 local windows (window shards of a multi-GPU MSM): one window per group (1) or one group (0).  Measured per shard of an
+  // 8-way sharded 2^20 G1 MSM (profiles/records/r02_msm_shard_times.txt): one group 2.12 .. 3.05 ms, one window per group
+  // 2.46 .. 3.22 ms — the overlapped reduce / Horner kernels of the upper window slow the lower window's bucket kernel by more
+  // than they hide
+  int tune_msm_tail_groups = 0;
   int tune_g1_prefetch = 1;    // G1 bucket kernel: cp.async double-buffered prefetch of the next point (1) or plain loads (0)
   int tune_pairing_chunks = 4; // independent Miller+final-exp chunks of a pairing batch kept in flight on 2 streams
   // G2 bucket kernel: 2 = accumulator in registers (255 regs, 2 blocks/SM); 3 = accumulator in shared memory, built

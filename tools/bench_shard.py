@@ -4,10 +4,12 @@
 
 Prints, for window sharding, the time of every shard (the step of the N-GPU run is the slowest one + gather + combine) and,
 for point-range sharding, the time of one n / n_shards slice with all windows."""
+import os
 import sys
 import numpy as np
 import torch
-import bls12_381_b200 as b
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import bls12_381_b200 as b  # noqa: E402
 from bls12_381_b200 import constants_host as ch
 
 ns = int(sys.argv[1]) if len(sys.argv) > 1 else 8

@@ -3,6 +3,7 @@
 
     python tools/exp_sweep.py pairing  [--log2n 16]     pairing batch: variant x coop_warps
     python tools/exp_sweep.py mul                        scalar-multiplication batch: n x mul_groups
+    python tools/exp_sweep.py products                   products of pairings (shared squaring) against n independent loops
 Prints one JSON object per measurement."""
 import argparse
 import json
@@ -47,7 +48,7 @@ def kernel_ms(eng, fn, stream):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["pairing", "mul"])
+    ap.add_argument("what", choices=["pairing", "mul", "products"])
     ap.add_argument("--log2n", type=int, default=16)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--warps", default="12")
@@ -87,6 +88,41 @@ def main():
                         ref = h
                     print(json.dumps({"what": "pairing", "n": n, "variant": var, "coop_warps": w,
                                       "ms": [round(x, 3) for x in ms], "kernels": km, "same_result": h == ref}), flush=True)
+        elif a.what == "products":
+            # Groth16 / BLS batch-verification shape: P products of T pairs each, one Gt per product
+            for T, P in ((3, 4096), (4, 4096), (3, 16384)):
+                n = T * P
+                pxy, pinf, _ = gen(1, n, 177 + T)
+                qxy, qinf, _ = gen(2, n, 178 + T)
+                out = torch.empty((P, 72), dtype=torch.int64, device=dev)
+                ml = torch.empty((n, 72), dtype=torch.int64, device=dev)
+                stream.synchronize()
+                shared = lambda: eng.pairing_product_batch_dev(pxy, pinf, qxy, qinf, T, P, out)  # noqa: E731
+
+                def loops():   # without the product mode: n independent Miller loops, then P final exponentiations (the T - 1
+                    eng.miller_loop_batch_dev(pxy, pinf, qxy, qinf, n, ml)       # Fp12 products per item are left out: favours
+                    eng.final_exponentiation_batch_dev(ml, P, out)               # this baseline)
+                ms_s = timed(torch, stream, shared, a.reps, flush)
+                ms_l = timed(torch, stream, loops, a.reps, flush)
+                print(json.dumps({"what": "pairing products", "terms": T, "products": P, "shared_squaring_ms": [round(x, 3) for x in ms_s],
+                                  "n_loops_ms": [round(x, 3) for x in ms_l], "speedup": round(min(ms_l) / min(ms_s), 3),
+                                  "kernels": kernel_ms(eng, shared, stream)}), flush=True)
+            # one product of 2^16 terms -> one MillerLoopResult
+            n = 1 << 16
+            pxy, pinf, _ = gen(1, n, 277)
+            qxy, qinf, _ = gen(2, n, 278)
+            one = torch.empty((1, 72), dtype=torch.int64, device=dev)
+            stream.synchronize()
+            fn = lambda: eng.multi_miller_loop_dev(pxy, pinf, qxy, qinf, n, one)  # noqa: E731
+            res = {}
+            for var in (0, 4):
+                eng.set_tuning("pairing_variant", var)
+                res[var] = timed(torch, stream, fn, a.reps, flush)
+                res["h%d" % var] = int(one.sum().item())
+            eng.set_tuning("pairing_variant", 0)
+            print(json.dumps({"what": "multi_miller_loop, one product", "n": n, "shared_squaring_ms": [round(x, 3) for x in res[0]],
+                              "n_loops_plus_product_ms": [round(x, 3) for x in res[4]], "speedup": round(min(res[4]) / min(res[0]), 3),
+                              "same_result": res["h0"] == res["h4"]}), flush=True)
         else:
             from bls12_381_b200 import constants_host as ch
             for k in (1, 2):
