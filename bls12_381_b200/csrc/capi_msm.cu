@@ -659,7 +659,10 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
   }
   size_t total = (size_t)pl.nloc * pl.nbuckets;
   // reduction geometry
-  constexpr int RB = sizeof(F) == sizeof(fp) ? 128 : 64;  // block size (smem: RB * PB)
+  // block size of the thread-per-chunk reduction (smem: RB * PB).  128 threads = the register footprint of ONE bucket-kernel block
+  // (G2: 128 x 255): a reduction block running under the next group's bucket kernel displaces exactly one of its blocks; with 64
+  // threads (round 1) twice as many blocks each displaced one — measured 28.3 vs 23.7 ms for the G2 2^20 step (msm_reduce = 1)
+  constexpr int RB = 128;
   int chunks = pl.nbuckets >= 2048 ? 2048 : pl.nbuckets;  // threads per window (power of two)
   if (chunks < RB) chunks = RB;
   int chunk = (pl.nbuckets + chunks - 1) / chunks;
@@ -667,9 +670,10 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
   int blocks_per_window = chunks / RB;
   // lane-cooperative reduction (default): groups of six lanes own RCHUNK buckets; partial counts per level: G, G/16, ... <= 8
   // tune_msm_reduce: 0 never, 1 only where the reduction is EXPOSED (the last window group of a call), 2 every group,
-  // -1 (default) = 1 for G1, 2 for G2.  Measured at 2^20 on one GPU: G1 8.99 (0) / 9.63 (2) ms — the cooperative kernels do more
-  // total work and compete with the pipe-bound bucket kernel of the next group; G2 30.1 (0) / 26.1 (2) ms.
-  const int reduce_mode = ctx->tune_msm_reduce >= 0 ? ctx->tune_msm_reduce : (sizeof(F) == sizeof(fp) ? 1 : 2);
+  // -1 (default) = 1.  Measured at 2^20 on one GPU: G1 8.85 (0) / 8.51 (1) / 9.50 (2) ms; G2 29.0 (0) / 23.7 (1) / 24.5 (2) ms with
+  // 128-thread blocks in the thread-per-chunk kernel (64-thread blocks: 28.3 ms in mode 1 — see RB above).  The cooperative
+  // kernels finish sooner but do more total work and take more of the GPU away from the pipe-bound bucket kernel of the next group.
+  const int reduce_mode = ctx->tune_msm_reduce >= 0 ? ctx->tune_msm_reduce : 1;
   const bool coop_reduce = reduce_mode != 0;
   constexpr int RCHUNK = 16, RFOLD = 16, RWARPS = 4;
   int r_chunk = pl.nbuckets < RCHUNK ? pl.nbuckets : RCHUNK, r_lo_bits = 0;

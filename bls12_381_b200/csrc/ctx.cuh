@@ -39,7 +39,7 @@ struct b200_ctx {
   // (K >= 128 pairs per thread) leave too few threads at this size.  Groundwork for larger N.
   int tune_msm_affine_levels = 0;
   // bucket reduction: 0 = one thread per chunk of buckets (round 1), 1 = lane-cooperative (six lanes per chunk, round 2) for
-  // the last — exposed — window group only, 2 = lane-cooperative for every group, -1 = by curve (G1: 1, G2: 2).  The CPU test
+  // the last — exposed — window group only (-1, the default, means this), 2 = lane-cooperative for every group.  The CPU test
   // harness defaults to 0 (every shuffle is two fiber barriers there: the emulated cooperative reduction costs minutes) and
   // switches it on for one small case (tests/test_msm_on_mock_cpu.py::test_cooperative_bucket_reduction).
 #ifdef B200_HOST_EMUL
