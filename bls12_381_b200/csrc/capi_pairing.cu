@@ -60,8 +60,51 @@ int final_exp_dev(b200_ctx *ctx, const void *in, size_t n, void *out) { return f
 // streams of the ctx.  Every thread of either kernel runs for milliseconds, so a single launch per kernel pays a
 // whole extra wave for the last, partially filled one (2^16 pairs = 1.73 waves of 148 SMs x 4 x 64 threads);
 // with independent chunks in flight the block scheduler back-fills the tail of one kernel with blocks of another.
+// Six-lane kernels, batch larger than one wave of groups (148 SMs x 12 warps x 5 = 8 880 pairs): the batch is cut into
+// `tune_coop_chunks` chunks that alternate between the two streams of the ctx.  Each kernel is one persistent block per SM and
+// every warp-turn runs for milliseconds, so a single launch per phase idles the SMs whose warps have one turn less (2^16 pairs =
+// 7.38 turns per warp: 91 of 148 blocks wait out the 8th turn, in both phases); with independent chunks in flight the blocks of
+// the other stream's next kernel take over an SM the moment a block exits.
+int coop_chunked(b200_ctx *ctx, const void *p, const void *pi, const void *q, const void *qi, size_t n, void *out, int chunks) {
+  int rc = arena_reserve(ctx, (size_t)19584 * n + 256);
+  if (rc != B200_OK) return rc;
+  char *co = arena_take<char>(ctx, (size_t)19584 * n);
+  B200_CUDA(ctx, cudaEventRecord(ctx->ev_sync[0], ctx->stream));
+  B200_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_sync[0], 0));
+  struct join_guard {   // every exit path (error returns included) re-joins the main stream with the side stream
+    b200_ctx *c;
+    ~join_guard() {
+      cudaEventRecord(c->ev_sync[1], c->stream2);
+      cudaStreamWaitEvent(c->stream, c->ev_sync[1], 0);
+    }
+  } join_on_exit{ctx};
+  // every chunk but the first is a whole number of waves, so that the kernels that finish LAST end on full rounds; the first
+  // chunk takes the remainder (its partial last round is back-filled by the blocks of the following chunk)
+  const size_t wave = (size_t)ctx->sm_count * (ctx->tune_coop_warps < 1 ? 1 : ctx->tune_coop_warps) * 5;
+  size_t per = (n / chunks) / wave * wave;
+  if (per < wave) per = wave;
+  const size_t first = n - (size_t)(chunks - 1) * per;   // n > 2 waves and chunks <= n / wave (caller) keep this positive
+  for (int c = 0; c < chunks; c++) {
+    size_t lo = c == 0 ? 0 : first + (size_t)(c - 1) * per, cnt = c == 0 ? first : per;
+    cudaStream_t st = (c & 1) ? ctx->stream2 : ctx->stream;
+    const char *cp = (const char *)p + 96 * lo, *cq = (const char *)q + 192 * lo;
+    const uint8_t *cpi = pi ? (const uint8_t *)pi + lo : nullptr, *cqi = qi ? (const uint8_t *)qi + lo : nullptr;
+    char *cout = (char *)out + 576 * lo, *cco = co + (size_t)19584 * lo;
+    rc = b200_pair_g2_prepare_v4(ctx, st, cq, cqi, cnt, cco);
+    if (rc == B200_OK) rc = b200_pair_coop_launch(ctx, st, 1, cp, cpi, cco, cqi, nullptr, cnt, cout);
+    if (rc == B200_OK) rc = b200_pair_coop_launch(ctx, st, 2, nullptr, nullptr, nullptr, nullptr, cout, cnt, cout);
+    if (rc != B200_OK) return rc;
+  }
+  return B200_OK;
+}
 int pairing_dev(b200_ctx *ctx, const void *p, const void *pi, const void *q, const void *qi, size_t n, void *out) {
-  if (ctx->coop_for(n)) return coop_from_affine(ctx, ctx->stream, p, pi, q, qi, n, out, true);
+  if (ctx->coop_for(n)) {
+    const size_t wave = (size_t)ctx->sm_count * (ctx->tune_coop_warps < 1 ? 1 : ctx->tune_coop_warps) * 5;
+    int chunks = ctx->tune_coop_chunks;
+    if ((size_t)chunks > n / wave) chunks = (int)(n / wave);
+    if (chunks > 1 && n > 2 * wave && ctx->tune_coop_split) return coop_chunked(ctx, p, pi, q, qi, n, out, chunks);
+    return coop_from_affine(ctx, ctx->stream, p, pi, q, qi, n, out, true);
+  }
   int chunks = ctx->tune_pairing_chunks;
   if (chunks < 1) chunks = 1;
   // chunking only pays when the batch exceeds one wave of resident threads (148 SMs x 4 blocks x 64 = 37 888): below

@@ -156,3 +156,21 @@ def test_shared_squaring_product_mode(eng, orc):
             assert np.array_equal(eng.pairing_product_batch(*a, terms, final_exp=True), orc.final_exponentiation(want, threads=4))
     finally:
         eng.set_tuning("coop_warps", 12)
+
+
+def test_six_lane_kernels_chunked_two_stream_schedule(eng, orc):
+    """full pairings of a batch larger than two waves of groups (one SM x 1 warp x 5 pairs on the mock): coop_chunks chunks
+    alternating between the two streams of the ctx, coefficients of all chunks in one arena block"""
+    rng = np.random.default_rng(17301)
+    _, pxy, pinf = util.rand_points(orc, 1, rng, 13)
+    _, qxy, qinf = util.rand_points(orc, 2, rng, 13)
+    pinf[3] = 1
+    qinf[11] = 1
+    eng.set_tuning("coop_warps", 1)
+    eng.set_tuning("coop_chunks", 3)
+    try:
+        got = eng.pairing_batch(pxy, pinf, qxy, qinf)
+    finally:
+        eng.set_tuning("coop_warps", 12)
+        eng.set_tuning("coop_chunks", 2)
+    assert np.array_equal(got, orc.pairing(pxy, pinf, qxy, qinf, threads=8))
