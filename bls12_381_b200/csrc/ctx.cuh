@@ -85,7 +85,9 @@ struct b200_ctx {
   // per warp = ceil(n / (4 * SMs)) clipped to 1..5), 1..5 forced items per warp, 6 = round 1's one warp per item
   int tune_mul_groups = 0;
   int tune_mul_groups_max_n = 9000;   // measured crossover with the thread-per-item kernel (G1): 8192 -> 5.05 vs 5.64 ms, 16384 -> 7.67 vs 5.63 ms
-  int tune_coop_chunks = 2;          // pairing batches of more than two waves: independent chunks on two streams (capi_pairing.cu)
+  // pairing batches of more than two waves: independent chunks on two streams (capi_pairing.cu).  2^16 pairs, whole-wave chunks:
+  // 1 chunk 54.6 ms, 2: 52.5, 3: 51.1, 4: 53.8
+  int tune_coop_chunks = 3;
   int tune_coop_warps = 12;          // warps per block (one block per SM) of the lane-cooperative pairing kernels, 1..16
   int tune_coop_split = 1;           // 1: Miller loop and final exponentiation of a pairing batch as two launches of the kernel
   bool coop_attr_done[7] = {};       // cudaFuncSetAttribute(max dynamic shared memory) done on this device, per kernel build

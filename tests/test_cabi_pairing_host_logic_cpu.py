@@ -172,5 +172,5 @@ def test_six_lane_kernels_chunked_two_stream_schedule(eng, orc):
         got = eng.pairing_batch(pxy, pinf, qxy, qinf)
     finally:
         eng.set_tuning("coop_warps", 12)
-        eng.set_tuning("coop_chunks", 2)
+        eng.set_tuning("coop_chunks", 3)
     assert np.array_equal(got, orc.pairing(pxy, pinf, qxy, qinf, threads=8))
