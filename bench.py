@@ -316,7 +316,8 @@ class Bench:
         AFFW, PROJW = 12 * k, 18 * k
         # --shard auto (default): the device-resident arm shards by WINDOW (every rank holds all points: fastest per shard, 3.05 vs
         # 3.67 ms at 8 GPUs), the end-to-end arm by POINT RANGE (a rank uploads only its slice: 17 MB instead of 135 MB per GPU)
-        mode = "window" if a.shard == "auto" else a.shard
+        # (2^24, config 5: point ranges for both arms — a rank then only generates and holds its own 2^21-point slice)
+        mode = ("window" if log2n <= 22 else "points") if a.shard == "auto" else a.shard
         mode_e2e = "points" if a.shard == "auto" else a.shard
         from bls12_381_b200.sharding import index_range
         t_gen = time.perf_counter()
