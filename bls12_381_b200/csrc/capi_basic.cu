@@ -504,6 +504,9 @@ int b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int value) {
     ctx->tune_pairing_variant = value;
   } else if (!strcmp(key, "coop_split")) {
     ctx->tune_coop_split = value != 0;
+  } else if (!strcmp(key, "coop_prepare_max")) {
+    if (value < 0) return B200_EINVAL;
+    ctx->tune_coop_prepare_max = value;
   } else if (!strcmp(key, "coop_chunks")) {
     if (value < 1 || value > 64) return B200_EINVAL;
     ctx->tune_coop_chunks = value;

@@ -17,11 +17,17 @@ DECL_VARIANT(v4)
 // pairing_coop.cu: flags 1 = Miller loop over prepared coefficients, 2 = final exponentiation (of `in` when bit 0 is clear)
 int b200_pair_coop_launch(b200_ctx *, cudaStream_t, int flags, const void *p, const void *pi, const void *coeffs,
                           const void *qi, const void *in, size_t n, void *out);
+int b200_pair_coop_prepare_launch(b200_ctx *, cudaStream_t, const void *q, const void *qi, size_t n, void *coeffs);
 int b200_pair_coop_product_launch(b200_ctx *, cudaStream_t, int final_exp, const void *p, const void *pi, const void *coeffs,
                                   const void *qi, int terms, size_t n_terms, size_t n_items, void *out);
 int b200_pair_coop_fold_launch(b200_ctx *, cudaStream_t, const void *in, size_t n, void *scratch, void *out);
 
 namespace {
+// G2 line coefficients for the six-lane kernels: small batches with six lanes per Q (latency), large ones one thread per Q
+int g2_prepare_on(b200_ctx *ctx, cudaStream_t st, const void *q, const void *qi, size_t n, void *coeffs) {
+  if (n <= (size_t)ctx->tune_coop_prepare_max) return b200_pair_coop_prepare_launch(ctx, st, q, qi, n, coeffs);
+  return b200_pair_g2_prepare_v4(ctx, st, q, qi, n, coeffs);
+}
 
 // The pairing kernels live in their own translation unit (pairing_v4.cu: 255 registers, 4 resident 64-thread blocks
 // per SM, Fp2 multiply = Karatsuba over fp_mul_c calls).  Lower register budgets (168 / 128) and the inlined /
@@ -34,7 +40,7 @@ int coop_from_affine(b200_ctx *ctx, cudaStream_t st, const void *p, const void *
   int rc = arena_reserve(ctx, (size_t)19584 * n + 256);
   if (rc != B200_OK) return rc;
   char *co = arena_take<char>(ctx, (size_t)19584 * n);
-  rc = b200_pair_g2_prepare_v4(ctx, st, q, qi, n, co);
+  rc = g2_prepare_on(ctx, st, q, qi, n, co);
   if (rc != B200_OK) return rc;
   if (with_final_exp && ctx->tune_coop_split) {
     rc = b200_pair_coop_launch(ctx, st, 1, p, pi, co, qi, nullptr, n, out);
@@ -157,7 +163,7 @@ int pairing_products_dev(b200_ctx *ctx, const void *p, const void *pi, const voi
   int rc = arena_reserve(ctx, (size_t)19584 * n + 256);
   if (rc != B200_OK) return rc;
   char *co = arena_take<char>(ctx, (size_t)19584 * n);
-  rc = b200_pair_g2_prepare_v4(ctx, ctx->stream, q, qi, n, co);
+  rc = g2_prepare_on(ctx, ctx->stream, q, qi, n, co);
   if (rc != B200_OK) return rc;
   return b200_pair_coop_product_launch(ctx, ctx->stream, final_exp, p, pi, co, qi, (int)terms, n, n_products, out);
 }
@@ -177,7 +183,7 @@ int multi_miller_dev(b200_ctx *ctx, const void *p, const void *pi, const void *q
   const char *co = (const char *)coeffs;
   if (!co && n) {
     char *c2 = arena_take<char>(ctx, (size_t)19584 * n);
-    rc = b200_pair_g2_prepare_v4(ctx, ctx->stream, q, qi, n, c2);
+    rc = g2_prepare_on(ctx, ctx->stream, q, qi, n, c2);
     if (rc != B200_OK) return rc;
     co = c2;
   }
@@ -252,7 +258,7 @@ int b200_fp12_product_dev(b200_ctx *ctx, const void *in, size_t n, void *out) {
 int b200_g2_prepare_dev(b200_ctx *ctx, const void *q, const void *q_inf, size_t n, void *coeffs) {
   CHECK_CTX(ctx);
   if (n && (!q || !coeffs)) return B200_EINVAL;
-  int rc = b200_pair_g2_prepare_v4(ctx, ctx->stream, q, q_inf, n, coeffs);
+  int rc = g2_prepare_on(ctx, ctx->stream, q, q_inf, n, coeffs);
   return rc != B200_OK ? rc : sync(ctx);
 }
 int b200_miller_loop_prepared_batch_dev(b200_ctx *ctx, const void *p, const void *p_inf, const void *coeffs,
@@ -272,7 +278,7 @@ int b200_g2_prepare(b200_ctx *ctx, const b200_g2_affine *q, const uint8_t *q_inf
   void *dq = stage_take(ctx, 192 * n), *dqi = q_inf ? stage_take(ctx, n) : nullptr, *dc = stage_take(ctx, 19584 * n);
   B200_CUDA(ctx, cudaMemcpyAsync(dq, q, 192 * n, cudaMemcpyHostToDevice, ctx->stream));
   if (q_inf) B200_CUDA(ctx, cudaMemcpyAsync(dqi, q_inf, n, cudaMemcpyHostToDevice, ctx->stream));
-  rc = b200_pair_g2_prepare_v4(ctx, ctx->stream, dq, dqi, n, dc);
+  rc = g2_prepare_on(ctx, ctx->stream, dq, dqi, n, dc);
   if (rc != B200_OK) return rc;
   B200_CUDA(ctx, cudaMemcpyAsync(coeffs, dc, 19584 * n, cudaMemcpyDeviceToHost, ctx->stream));
   return sync(ctx);

@@ -88,9 +88,12 @@ struct b200_ctx {
   // pairing batches of more than two waves: independent chunks on two streams (capi_pairing.cu).  2^16 pairs, whole-wave chunks:
   // 1 chunk 54.6 ms, 2: 52.5, 3: 51.1, 4: 53.8
   int tune_coop_chunks = 3;
+  // G2 line coefficients for the six-lane kernels: batches of at most this many pairs use the six-lanes-per-Q kernel
+  // (k_coop_g2_prepare: latency), larger ones one thread per Q (k_g2_prepare: throughput)
+  int tune_coop_prepare_max = 5000;   // measured: 1024 pairs 1.22 vs 2.28 ms, 4096: 1.63 vs 2.29, 8192: 3.67 vs 2.32
   int tune_coop_warps = 12;          // warps per block (one block per SM) of the lane-cooperative pairing kernels, 1..16
   int tune_coop_split = 1;           // 1: Miller loop and final exponentiation of a pairing batch as two launches of the kernel
-  bool coop_attr_done[7] = {};       // cudaFuncSetAttribute(max dynamic shared memory) done on this device, per kernel build
+  bool coop_attr_done[8] = {};       // cudaFuncSetAttribute(max dynamic shared memory) done on this device, per kernel build
   // multi-GPU (capi_multi.cu): NCCL communicator of this rank, and a (world + 1) x 576-byte exchange buffer on the device
   void *nccl_comm = nullptr;
   int comm_rank = 0, comm_world = 1;
