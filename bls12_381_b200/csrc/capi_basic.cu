@@ -494,6 +494,9 @@ int b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int value) {
     ctx->tune_g1_glv = value;
   } else if (!strcmp(key, "msm_tail_groups")) {
     ctx->tune_msm_tail_groups = value != 0;
+  } else if (!strcmp(key, "msm_reduce_min_chunk")) {
+    if (value < 1 || value > 64) return B200_EINVAL;
+    ctx->tune_msm_reduce_min_chunk = value;
   } else if (!strcmp(key, "msm_reduce")) {
     if (value < -1 || value > 2) return B200_EINVAL;
     ctx->tune_msm_reduce = value;

@@ -663,7 +663,14 @@ int msm_dev(b200_ctx *ctx, const void *points, const void *inf, const void *scal
   // (G2: 128 x 255): a reduction block running under the next group's bucket kernel displaces exactly one of its blocks; with 64
   // threads (round 1) twice as many blocks each displaced one — measured 28.3 vs 23.7 ms for the G2 2^20 step (msm_reduce = 1)
   constexpr int RB = 128;
-  int chunks = pl.nbuckets >= 2048 ? 2048 : pl.nbuckets;  // threads per window (power of two)
+  // threads per window (power of two): at most 2048, at least `tune_msm_reduce_min_chunk` buckets each — every 128 threads are one
+  // partial sum that k_msm_horner adds up serially (3 us each), so narrow windows (2^11 buckets: small MSMs) must not be cut into
+  // 16 one-bucket-per-thread blocks
+  int chunks = pl.nbuckets >= 2048 ? 2048 : pl.nbuckets;
+  {
+    int min_chunk = ctx->tune_msm_reduce_min_chunk < 1 ? 1 : ctx->tune_msm_reduce_min_chunk;
+    while (chunks > RB && pl.nbuckets / chunks < min_chunk) chunks >>= 1;
+  }
   if (chunks < RB) chunks = RB;
   int chunk = (pl.nbuckets + chunks - 1) / chunks;
   if (chunk < 1) chunk = 1;

@@ -52,6 +52,7 @@ struct b200_ctx {
   // 2.46 .. 3.22 ms — the overlapped reduce / Horner kernels of the upper window slow the lower window's bucket kernel by more
   // than they hide
   int tune_msm_tail_groups = 0;
+  int tune_msm_reduce_min_chunk = 8;   // buckets per thread of the thread-per-chunk reduction, at least (capi_msm.cu)
   int tune_g1_prefetch = 1;    // G1 bucket kernel: cp.async double-buffered prefetch of the next point (1) or plain loads (0)
   int tune_pairing_chunks = 4; // independent Miller+final-exp chunks of a pairing batch kept in flight on 2 streams
   // G2 bucket kernel: 2 = accumulator in registers (255 regs, 2 blocks/SM); 3 = accumulator in shared memory, built
