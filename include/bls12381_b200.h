@@ -74,11 +74,21 @@ uint64_t b200_ctx_launch_count(const b200_ctx *ctx);
  * '\n' into `names`, and returns the number of records since the last set_timing call (>= 0). */
 int b200_ctx_set_timing(b200_ctx *ctx, int on);
 int b200_ctx_get_timing(b200_ctx *ctx, char *names, size_t names_len, float *ms, int max);
-/* tuning knobs by name: "msm_window" (0 = auto, else 2..24), "g1_glv" (0 off, 1 on, 2 auto = on for window-sharded calls), "msm_affine_levels" (-1 auto, 0..3 batched-affine
- * tree levels before the bucket kernel; default 0), "g1_prefetch" (0|1), "msm_reduce" (bucket reduction: 0 one thread per chunk, 1 lane-cooperative for the last window group, 2 for every group, -1 by curve = default), "msm_tail_groups" (0|1), "g2_acc_blocks" (G2 bucket kernel variant: 2 registers,
- * 3 shared-memory accumulator built for 3 blocks/SM, 4 shared-memory accumulator at 2 blocks/SM = default), "pairing_chunks" (1..64 independent chunks of a
- * pairing batch in flight), "pairing_variant" (0 = chosen by batch size, default; 7 = six lanes per pairing; 4 = one thread per pairing), "coop_warps" (1..12 warps per block of the
- * six-lane pairing kernels).  Unknown key or bad value -> B200_EINVAL. */
+/* tuning knobs by name (defaults are the measured best on B200; DESIGN.md has the numbers).  Unknown key or bad value -> B200_EINVAL.
+ *   MSM:      "msm_window" (0 = auto, else 2..24) · "g1_glv" (0 off = default, 1 on, 2 on for window-sharded calls) ·
+ *             "msm_affine_levels" (-1 auto, 0..3 batched-affine tree levels before the bucket kernel; default 0) · "g1_prefetch" (0|1) ·
+ *             "msm_reduce" (bucket reduction: 0 one thread per chunk, 1 lane-cooperative for the exposed last window group = default
+ *             (also -1), 2 lane-cooperative everywhere) · "msm_reduce_min_chunk" (1..64 buckets per thread at least, default 8) ·
+ *             "msm_tail_groups" (2-3 local windows: 0 one group = default, 1 one window per group) ·
+ *             "g2_acc_blocks" (G2 bucket kernel: 2 registers, 3 shared-memory accumulator built for 3 blocks/SM, 4 shared-memory accumulator
+ *             at 2 blocks/SM = default)
+ *   pairing:  "pairing_variant" (0 = six lanes per pairing at every batch size = default, 7 the same explicitly, 4 = one thread per pairing) ·
+ *             "coop_warps" (1..12 warps per block of the six-lane kernels) · "coop_split" (Miller loop and final exponentiation as two
+ *             launches, default 1) · "coop_chunks" (1..64 whole-wave chunks on two streams for batches of more than two waves, default 3) ·
+ *             "coop_prepare_max" (largest batch whose G2 line coefficients come from the six-lanes-per-Q kernel, default 5000) ·
+ *             "pairing_chunks" (1..64 chunks of a batch of the one-thread-per-pairing kernels)
+ *   scalar multiplication batches: "mul_groups" (-1 thread per item, 0 auto = default, 1..5 items per warp of the six-lane group kernel,
+ *             6 one warp per item) · "mul_groups_max_n" (largest batch for the group kernel, default 9000) */
 int b200_ctx_set_tuning(b200_ctx *ctx, const char *key, int value);
 /* MSM tuning: window bits c (0 = automatic from n, else 2..24); B200_OK or B200_EINVAL (same as set_tuning("msm_window")) */
 int b200_ctx_set_msm_window(b200_ctx *ctx, int c);
