@@ -22,6 +22,7 @@
 // Fp2 multiply of this unit: lazy reduction with row-alternated products / reductions (fp2.cuh; measured best for the
 // G2 bucket kernel in round 2: 30.1 vs 31.3 ms at 2^20)
 #define B200_FP2_LAZY3 1
+#include <cmath>
 #include "ctx.cuh"
 #include "curve.cuh"
 #include "curve_warp.cuh"
@@ -608,28 +609,40 @@ __global__ void k_store_identity(char *out) {
 
 inline unsigned nblk(size_t n, unsigned b) { return (unsigned)((n + b - 1) / b); }
 
-// is window width c a good choice for n points?  The scalars have 255 bits: the TOP window holds tb = 255 - c*floor(255/c)
-// of them, i.e. only 2^tb distinct digits with n / 2^tb points each.  That is fine when the window is (almost) full, when
-// those buckets are so heavy that the block-parallel giant path takes them (>= GIANT_BUCKET points), or when they are not
-// much heavier than an ordinary bucket — but in between a handful of THREADS walk hundreds of points each
-// (measured: 2^17 points, c = 13, tb = 8: 256 buckets of 512 points, bucket kernel 8.8 ms instead of 2.0 ms with c = 14).
+// is window width c a good choice for n points?  One thread walks one bucket, so what matters is the LONGEST bucket that is
+// not handed to the block-parallel giant path (>= GIANT_BUCKET points).  The scalars are uniform below q (255 bits), so only the
+// TOP window is special: it holds the top tb = 255 - c*floor(255/c) bits, i.e. qt = q / 2^shift possible values, and its last two
+// buckets are lighter than the rest (b = floor(qt) covers only the fractional part f of a value range, and a carry out of the
+// window below is rarer there).  Expected populations, n scalars:   ordinary top bucket n / qt;   digit B = floor(qt):
+// n (f (1 - pc) + 1/2) / qt;   digit B + 1: n f pc / qt   with pc = max(0, f - 1/2) / f.   Each of them must be either short
+// (<= 4 x the average bucket of the other windows, or <= 96 points: ~1 ms on one thread, the size of the fixed costs) or safely
+// above the giant threshold.  Measured before this rule (round 2, profiles/records/r02_g1_msm_small_windows.txt): 2^14 points,
+// c = 11: top buckets of 4580, 4556, 4461 and 547 points — the 547-point one alone kept a thread busy for 5.5 ms (MSM 7.9 ms;
+// c = 12: 2.7 ms); 2^13 points, c = 9: 11.3 ms (c = 13: 2.9 ms).
 // tb = 0 (c divides 255 = 3 * 5 * 17) is the worst case: the signed-digit carry of the full top window opens one more
 // window whose single bucket collects half of all points.
 bool window_ok(int c, size_t n) {
   int tb = 255 - c * (255 / c);
   if (tb == 0) return false;
-  size_t heavy = n >> tb, avg = n >> (c - 1);
-  return tb >= c - 2 || heavy >= GIANT_BUCKET || heavy <= 4 * avg + 8;
+  const int shift = c * (255 / c);
+  const double qt = ldexp((double)0x73eda753299d7d48ull, 192 - shift);   // q / 2^shift (src/scalar.rs:76-81, top 64 bits)
+  const double B = floor(qt), f = qt - B, pc = f > 0.5 ? (f - 0.5) / f : 0.0;
+  const double avg = (double)n / (double)((size_t)1 << (c - 1));
+  const double lim = 4.0 * avg + 8.0 > 96.0 ? 4.0 * avg + 8.0 : 96.0;
+  auto fine = [&](double p) { return p <= lim || p >= 1.1 * (double)GIANT_BUCKET; };
+  const double generic = (double)n / qt, pB = (double)n * (f * (1.0 - pc) + 0.5) / qt, pB1 = (double)n * f * pc / qt;
+  return fine(generic) && fine(B >= 1.0 ? pB : 0.0) && fine(pB1);
 }
 int auto_window(size_t n) {
-  // minimise  W * n (bucket adds) + W * 2^(c-1) * ~3 (reduction) ; measured sweet spots on B200
+  // minimise  W * n (bucket adds) + W * 2^(c-1) * ~3 (reduction) ; measured sweet spots on B200.  Wider windows first: for small
+  // n the step is latency (longest bucket, Horner chain), and more, shorter buckets win (2^14: c = 12 2.7 ms, c = 9 4.8 ms)
   int lg = 0;
   while (((size_t)1 << (lg + 1)) <= n) lg++;
   int c = lg - 4;
   if (c < 4) c = 4;
   if (c > 16) c = 16;
-  const int order[4] = {0, 1, -1, 2};
-  for (int k = 0; k < 4; k++) {
+  const int order[6] = {0, 1, 2, 3, 4, -1};
+  for (int k = 0; k < 6; k++) {
     int cc = c + order[k];
     if (cc >= 4 && cc <= 18 && window_ok(cc, n)) return cc;
   }
