@@ -174,3 +174,19 @@ def test_six_lane_kernels_chunked_two_stream_schedule(eng, orc):
         eng.set_tuning("coop_warps", 12)
         eng.set_tuning("coop_chunks", 3)
     assert np.array_equal(got, orc.pairing(pxy, pinf, qxy, qinf, threads=8))
+
+
+@pytest.mark.parametrize("prepare_max", [0, 5000])
+def test_g2_prepare_both_kernels_on_mock(eng, orc, prepare_max):
+    """G2Prepared coefficients from the one-thread-per-Q kernel and from the six-lanes-per-Q kernel (k_coop_g2_prepare: shared-
+    memory board, per-group __syncwarp on the fiber scheduler), limb for limb against the oracle; identity = generator's coefficients"""
+    rng = np.random.default_rng(17400)
+    _, qxy, qinf = util.rand_points(orc, 2, rng, 7)
+    qinf[3] = 1
+    eng.set_tuning("coop_prepare_max", prepare_max)
+    try:
+        co = eng.g2_prepare(qxy, qinf)
+    finally:
+        eng.set_tuning("coop_prepare_max", 5000)
+    for i in range(7):
+        assert np.array_equal(co[i], orc.g2_prepare(qxy[i], qinf[i])), i

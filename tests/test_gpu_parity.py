@@ -461,6 +461,25 @@ def test_g2_prepared(eng, orc):
     assert eq(ml.cpu().numpy().view(np.uint64), orc.miller_loop(pxy, pinf, qxy, qinf, threads=4))
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("prepare_max", [0, 1000000])
+def test_g2_prepared_both_kernels(eng, orc, prepare_max):
+    """the two kernels behind b200_g2_prepare — one thread per Q (pairing_v4.cu, large batches) and six lanes per Q
+    (k_coop_g2_prepare, small batches; tuning key coop_prepare_max picks) — give the same 68 coefficient triples as the oracle,
+    identity included (prepared as the generator, src/pairings.rs:528-544); ragged batch (not a multiple of 5 Qs per warp)"""
+    rng = np.random.default_rng(1410 + (prepare_max > 0))
+    n = 23
+    _, qxy, qinf = util.rand_points(orc, 2, rng, n)
+    qinf[5] = 1
+    eng.set_tuning("coop_prepare_max", prepare_max)
+    try:
+        co = eng.g2_prepare(qxy, qinf)
+    finally:
+        eng.set_tuning("coop_prepare_max", 5000)
+    for i in range(n):
+        assert eq(co[i], orc.g2_prepare(qxy[i], qinf[i])), i
+
+
 @pytest.mark.parametrize("k,n", [(1, 40000), (2, 12000)])
 def test_msm_giant_buckets(eng, orc, k, n):
     """skewed scalars: all-equal scalars put every point of a window into ONE bucket (>= 1023 points -> split across
