@@ -520,7 +520,7 @@ class Bench:
                     # the model's 16 020 FpM per pairing, so the three launches are timed together
                     fpm = fpm_exec = 16020.0 * n_local
                     alg_bytes = (96 + 192 + 576) * n_local
-                    avg_ms += sum(per_kernel.get("k_g2_prepare", [])) / steps
+                    avg_ms += (sum(per_kernel.get("k_g2_prepare", [])) + sum(per_kernel.get("k_coop_g2_prepare", []))) / steps
                     if avg_ms > 1.02 * ms_per_step:      # chunks on two streams: the launches overlap, their event times add up to
                         avg_ms, chunked_v4 = ms_per_step, True   # more than the step — the three kernels ARE the step: time that
                 else:
