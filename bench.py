@@ -386,6 +386,42 @@ class Bench:
             if not torch.equal(ref, out):
                 raise SystemExit("bench.py: ranks disagree on the combined MSM result (rank %d)" % rank)
             verified = True if verified is None else verified
+        split_checked = None
+        if world > 1 and wl in ("g1_msm", "g2_msm") and (log2n > 22 or os.environ.get("B200_BENCH_FORCE_SPLIT_CHECK")):
+            # sizes with no single-GPU / oracle comparison (config 5, 2^24): a size-independent property instead — the MSM over all
+            # points must equal MSM(first half of every rank's range) + MSM(second half), computed by the same sharded call with the
+            # other half flagged as identities (different bucket populations, same group element).  Outside the timed region.
+            try:
+                r_lo, r_hi = index_range(n, rank, world)
+                mid = (r_lo + r_hi) // 2
+                parts = torch.empty((2, PROJW), dtype=torch.int64, device=dev)
+                for half, (a0, a1) in enumerate(((mid, r_hi), (r_lo, mid))):       # flag [a0, a1) as identities
+                    inf_h = inf.clone()
+                    inf_h[a0:a1] = 1
+                    if mode == "window":                                            # every rank holds all points: flag the same halves everywhere
+                        for rr in range(world):
+                            q_lo, q_hi = index_range(n, rr, world)
+                            q_mid = (q_lo + q_hi) // 2
+                            b0, b1 = ((q_mid, q_hi), (q_lo, q_mid))[half]
+                            inf_h[b0:b1] = 1
+                    tmp = torch.empty((1, PROJW), dtype=torch.int64, device=dev)
+                    eng.msm_sharded_dev(k, xy, inf_h, sc, n, tmp, mode=mode)
+                    parts[half].copy_(tmp[0])
+                total = torch.empty((1, PROJW), dtype=torch.int64, device=dev)
+                eng.sum_dev(k, parts, 2, total)
+                both = torch.cat([out, total]).contiguous()
+                axy = torch.empty((2, AFFW), dtype=torch.int64, device=dev)
+                ainf = torch.empty(2, dtype=torch.uint8, device=dev)
+                eng.batch_normalize_dev(k, both, 2, axy, ainf)
+                torch.cuda.synchronize()
+                split_checked = bool(torch.equal(axy[0], axy[1]) and ainf[0] == ainf[1] and int(ainf[0]) == 0)
+            except Exception as e:                                                   # a broken CHECK must not hide the measurement
+                split_checked = "not run: %s" % (str(e)[:120],)
+            if split_checked is False:
+                raise SystemExit("bench.py: MSM(all) != MSM(first halves) + MSM(second halves) on rank %d" % rank)
+            # re-run the real call so that `out` and the warm state are those of the timed configuration
+            step_device()
+            self.barrier()
         eng.set_timing(True)
         launches0 = eng.launches
         sampler = ClockSampler(self.local_rank)
@@ -576,7 +612,8 @@ class Bench:
                                         mode + "-sharded (device-resident arm) / " + mode_e2e + "-sharded (e2e arm) inside the library: "
                                         "shard + one ncclAllGather of the partial sums + combine on one stream")),
                           "l2": "256 MiB buffer written between timed steps (L2 flush)",
-                          "input_generation_s": t_gen, "seed": hex(seed), "sharded_result_checked": verified},
+                          "input_generation_s": t_gen, "seed": hex(seed), "sharded_result_checked": verified,
+                          "split_sum_checked": split_checked},
                "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu}
         return res
 
